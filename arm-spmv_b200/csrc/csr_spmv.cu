@@ -1,0 +1,670 @@
+// csr_spmv.cu -- CSR y (+)= A x for sm_100a.
+//
+// Replaces CSRMatrixMatVector (src/mat_vec.cpp:44-67) and the per-block body
+// CSRMatrixMatVectorNumaThread (src/mat_vec.cpp:507-530).
+//
+// Kernels (all HBM-bound; 12 B per stored entry must be streamed once, x is gathered through
+// L1/L2, tensor cores are irrelevant at 0.15 flop/B):
+//
+//  STREAM  the B200 path.  Persistent CTAs, one per SM.  Each warp owns tiles of 32
+//          consecutive rows, round-robin over the grid so that all SMs sweep the matrix as one
+//          moving front (the x working set of the front stays in L2).  The tile's val[] and
+//          col_ind[] ranges are contiguous in memory, so lane 0 fetches them with two 1-D TMA
+//          bulk copies (cp.async.bulk, SASS UBLKCP) into a per-warp ring of shared-memory
+//          stages guarded by mbarriers; no registers, no L1 pollution, every byte of a 128 B
+//          line used once.  Each lane then walks ITS row in shared memory left to right.
+//          Summation order = the reference's: s=0, s+=v_j*x_j in stored order, one
+//          y_i (+)= s, unfused mul/add  ->  bit-identical to the x86 reference.
+//  VECTOR  L lanes per row straight from global (L in {1,2,4,8,16,32}; L=1 is the scalar
+//          kernel).  Order: lane l sums entries l, l+L, ... in order, then a butterfly over
+//          lanes.  L=1 is again the reference's order.
+//  MERGE   nnz-balanced: fixed-size runs of entries per warp regardless of row boundaries,
+//          products reduced with a segmented warp scan, rows that cross a run boundary
+//          completed through a carry array and a fix-up pass.  For power-law rows.
+//
+// The plan picks kernel and L from the row-length histogram (thsp_csr_plan_create).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace thsp {
+
+// =============================================================== VECTOR / SCALAR ==========
+template <typename V, int L>
+__global__ void __launch_bounds__(256) csr_vector_kernel(int nrow, const int* __restrict__ row_ptr,
+                                                         const int* __restrict__ col, const V* __restrict__ val,
+                                                         const V* __restrict__ x, V* __restrict__ y, int accumulate)
+{
+    const int rows_per_cta = 256 / L;
+    const int sub = threadIdx.x % L;
+    const int row = blockIdx.x * rows_per_cta + threadIdx.x / L;
+    V sum = V(0);
+    if (row < nrow) {
+        const int rs = __ldg(row_ptr + row), re = __ldg(row_ptr + row + 1);
+        int j = rs + sub;
+        // Narrow lane counts walk along cache lines over several iterations: let L1 keep them.
+        // Wide ones consume whole lines per instruction: stream past L1.
+        auto ldc = [&](const int* p) { return L <= 4 ? __ldg(p) : ld_stream(p); };
+        auto ldv = [&](const V* p) { return L <= 4 ? __ldg(p) : ld_stream(p); };
+        // two entries in flight per lane
+        for (; j + L < re; j += 2 * L) {
+            int c0 = ldc(col + j), c1 = ldc(col + j + L);
+            V v0 = ldv(val + j), v1 = ldv(val + j + L);
+            V x0 = ld_gather(x + c0), x1 = ld_gather(x + c1);
+            sum = add_rn(sum, mul_rn(v0, x0));
+            sum = add_rn(sum, mul_rn(v1, x1));
+        }
+        if (j < re) sum = add_rn(sum, mul_rn(ldv(val + j), ld_gather(x + ldc(col + j))));
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    if (row < nrow && sub == 0) y[row] = accumulate ? add_rn(y[row], sum) : sum;
+}
+
+template <typename V, int L>
+static int launch_vector(int nrow, const int* rp, const int* col, const V* val, const V* x, V* y, int acc, cudaStream_t s)
+{
+    const int rows_per_cta = 256 / L;
+    csr_vector_kernel<V, L><<<div_up(nrow, rows_per_cta), 256, 0, s>>>(nrow, rp, col, val, x, y, acc);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename V>
+static int run_vector(int lanes, int nrow, const int* rp, const int* col, const V* val, const V* x, V* y, int acc,
+                      cudaStream_t s)
+{
+    switch (lanes) {
+        case 1: return launch_vector<V, 1>(nrow, rp, col, val, x, y, acc, s);
+        case 2: return launch_vector<V, 2>(nrow, rp, col, val, x, y, acc, s);
+        case 4: return launch_vector<V, 4>(nrow, rp, col, val, x, y, acc, s);
+        case 8: return launch_vector<V, 8>(nrow, rp, col, val, x, y, acc, s);
+        case 16: return launch_vector<V, 16>(nrow, rp, col, val, x, y, acc, s);
+        case 32: return launch_vector<V, 32>(nrow, rp, col, val, x, y, acc, s);
+    }
+    set_error("csr vector kernel: lanes must be 1,2,4,8,16 or 32 (got %d)", lanes);
+    return 2;
+}
+
+// ======================================================================== STREAM ==========
+// Shared memory per warp:  S stages of { V val[CH+8]; int col[CH+8]; }  + row-bound ring
+// { int rs[S][32]; int re[S][32]; } + S mbarriers.  CH (entries per stage) is a multiple of 4
+// so that every chunk after a tile's first starts 16 B aligned; the first chunk starts at the
+// tile's first entry rounded DOWN to a multiple of 4 (entries before it are fetched and
+// ignored), and the bulk copy never reads past nnz rounded down to 4 -- the last <=3 entries
+// of the arrays are fetched with ordinary loads.
+struct StreamCfg {
+    int warps;   // per CTA
+    int stages;  // ring depth per warp
+    int chunk;   // CH
+};
+
+template <typename V>
+__host__ __device__ inline size_t stream_warp_bytes(int stages, int chunk)
+{
+    size_t per_stage = (size_t)(chunk + 8) * (sizeof(V) + sizeof(int));
+    size_t ring = (size_t)stages * (64 * sizeof(int) + sizeof(uint64_t));
+    size_t b = (size_t)stages * per_stage + ring;
+    return (b + 127) & ~(size_t)127;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(512, 1)
+    csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                      const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    unsigned char* base = smem_raw + (size_t)warp * stream_warp_bytes<V>(S, CH);
+    const int stage_elems = CH + 8;
+    V* s_val = reinterpret_cast<V*>(base);                                             // [S][CH+8]
+    int* s_col = reinterpret_cast<int*>(base + (size_t)S * stage_elems * sizeof(V));    // [S][CH+8]
+    int* s_rs = s_col + (size_t)S * stage_elems;                                       // [S][32]
+    int* s_re = s_rs + S * 32;                                                         // [S][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_re + S * 32);                        // [S]
+
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(bar + s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const int num_tiles = (nrow + 31) >> 5;
+    const int GW = gridDim.x * W;
+    const int gw = blockIdx.x * W + warp;
+    const int nnz_al = nnz & ~3;
+    const uint64_t pol = policy_evict_first();
+
+    // ---- producer cursor (warp-uniform) -------------------------------------------------
+    int p_tile = gw, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
+    bool p_open = false;
+    int pf_rs = 0, pf_re = 0;  // row bounds of p_tile, fetched one step ahead
+    if (p_tile < num_tiles) {
+        int r = p_tile * 32 + lane;
+        pf_rs = __ldg(row_ptr + min(r, nrow));
+        pf_re = __ldg(row_ptr + min(r + 1, nrow));
+    }
+
+    auto produce = [&]() {
+        if (p_tile >= num_tiles) return;
+        if (!p_open) {
+            s_rs[p_slot * 32 + lane] = pf_rs;
+            s_re[p_slot * 32 + lane] = pf_re;
+            const int ts = __shfl_sync(0xffffffffu, pf_rs, 0);
+            p_te = __shfl_sync(0xffffffffu, pf_re, 31);
+            p_al = ts & ~3;
+            p_nch = max(1, (p_te - p_al + CH - 1) / CH);
+            p_chunk = 0;
+            p_open = true;
+            const int nt = p_tile + GW;  // bounds of the tile after this one
+            if (nt < num_tiles) {
+                int r = nt * 32 + lane;
+                pf_rs = __ldg(row_ptr + min(r, nrow));
+                pf_re = __ldg(row_ptr + min(r + 1, nrow));
+            }
+        }
+        const int g0 = p_al + p_chunk * CH;
+        const int g1 = min(g0 + CH, p_te);
+        const int t1 = min((g1 + 3) & ~3, nnz_al);
+        const int nt = max(t1 - g0, 0);
+        V* dv = s_val + (size_t)p_stage * stage_elems;
+        int* dc = s_col + (size_t)p_stage * stage_elems;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar + p_stage, (unsigned)nt * (unsigned)(sizeof(V) + sizeof(int)));
+            if (nt > 0) {
+                bulk_g2s(dv, val + g0, (unsigned)nt * (unsigned)sizeof(V), bar + p_stage, pol);
+                bulk_g2s(dc, col + g0, (unsigned)nt * (unsigned)sizeof(int), bar + p_stage, pol);
+            }
+        }
+        if (g1 > nnz_al) {  // ragged end of the arrays: at most 3 entries
+            const int g = max(g0, nnz_al) + lane;
+            if (g < g1) {
+                dv[g - g0] = val[g];
+                dc[g - g0] = col[g];
+            }
+        }
+        p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+        if (++p_chunk == p_nch) {
+            p_tile += GW;
+            p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
+            p_open = false;
+        }
+    };
+
+    for (int i = 0; i < S - 1; ++i) produce();
+
+    // ---- consumer ---------------------------------------------------------------------
+    int c_slot = 0, c_stage = 0;
+    unsigned c_parity = 0;
+    for (int tile = gw; tile < num_tiles; tile += GW) {
+        produce();  // may open this very tile when S == 1
+        const int row = tile * 32 + lane;
+        const int rs = s_rs[c_slot * 32 + lane];
+        const int re = s_re[c_slot * 32 + lane];
+        c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
+        const int ts = __shfl_sync(0xffffffffu, rs, 0);
+        const int te = __shfl_sync(0xffffffffu, re, 31);
+        const int al = ts & ~3;
+        const int nch = max(1, (te - al + CH - 1) / CH);
+        V yold = V(0);
+        if (accumulate && row < nrow) yold = y[row];
+        V sum = V(0);
+        for (int c = 0; c < nch; ++c) {
+            if (c > 0) produce();
+            mbar_wait(bar + c_stage, c_parity);
+            __syncwarp();
+            const int g0 = al + c * CH;
+            const int g1 = min(g0 + CH, te);
+            const V* sv = s_val + (size_t)c_stage * stage_elems - g0;
+            const int* sc = s_col + (size_t)c_stage * stage_elems - g0;
+            const int lo = max(rs, g0), hi = min(re, g1);
+            int j = lo;
+            for (; j + 3 < hi; j += 4) {
+                const int c0 = sc[j], c1 = sc[j + 1], c2 = sc[j + 2], c3 = sc[j + 3];
+                const V x0 = ld_gather(x + c0), x1 = ld_gather(x + c1), x2 = ld_gather(x + c2), x3 = ld_gather(x + c3);
+                sum = add_rn(sum, mul_rn(sv[j], x0));
+                sum = add_rn(sum, mul_rn(sv[j + 1], x1));
+                sum = add_rn(sum, mul_rn(sv[j + 2], x2));
+                sum = add_rn(sum, mul_rn(sv[j + 3], x3));
+            }
+            for (; j < hi; ++j) sum = add_rn(sum, mul_rn(sv[j], ld_gather(x + sc[j])));
+            __syncwarp();
+            c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
+            if (c_stage == 0) c_parity ^= 1u;
+        }
+        if (row < nrow) y[row] = accumulate ? add_rn(yold, sum) : sum;
+    }
+}
+
+template <typename V>
+static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
+                      const V* x, V* y, int acc, cudaStream_t s)
+{
+    THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
+                 "csr stream kernel needs 16-byte aligned val/col_ind");
+    THSP_REQUIRE(cfg.chunk % 4 == 0 && cfg.chunk >= 32 && cfg.stages >= 1 && cfg.warps >= 1 && cfg.warps <= 16,
+                 "bad stream configuration");
+    size_t smem = stream_warp_bytes<V>(cfg.stages, cfg.chunk) * (size_t)cfg.warps;
+    THSP_REQUIRE(smem <= 227 * 1024, "stream configuration exceeds 227 KB of shared memory");
+    static size_t configured[2] = {0, 0};
+    size_t& cur = configured[sizeof(V) == 8 ? 0 : 1];
+    if (smem > cur) {
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cur = 227 * 1024;
+    }
+    const int num_tiles = (nrow + 31) / 32;
+    int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
+    if (grid < 1) grid = 1;
+    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// Stage size from the mean row length: one 32-row tile should fit one stage.
+template <typename V>
+static StreamCfg default_stream_cfg(int nrow, int nnz)
+{
+    double mean = nrow > 0 ? (double)nnz / nrow : 0.0;
+    int want = (int)(mean * 32.0 * 1.05) + 16;
+    int chunk = 128;
+    while (chunk < want && chunk < 2048) chunk += 128;
+    StreamCfg c;
+    c.chunk = chunk;
+    c.warps = 8;
+    c.stages = 2;
+    // use what shared memory allows: prefer deeper rings, then more warps
+    auto fits = [&](int w, int s) { return stream_warp_bytes<V>(s, chunk) * (size_t)w <= 200 * 1024; };
+    while (c.stages < 4 && fits(c.warps, c.stages + 1)) ++c.stages;
+    while (c.warps < 16 && fits(c.warps + 1, c.stages)) ++c.warps;
+    while (c.warps > 1 && !fits(c.warps, c.stages)) --c.warps;
+    return c;
+}
+
+// ========================================================================= MERGE ==========
+// nnz-balanced: run t = entries [t*kMergeRun, (t+1)*kMergeRun) belongs to one warp whatever
+// the row boundaries are.
+//   1. binary search: row_lo = the row holding the run's first entry;
+//   2. every later row that STARTS inside the run scatters its id to mark[start - e0] in shared
+//      memory (atomicMax, so that of several empty rows starting at one entry the last - the
+//      non-empty one - wins); a running max over the marks gives each entry's row;
+//   3. 32 entries at a time: products, segmented inclusive scan (segments = equal rows), the
+//      segment still open at the end of a group is chained into the next group;
+//   4. a row that ends inside the run is added into y by the lane holding its last entry -
+//      unless it began in an earlier run, in which case its partial goes to carry slot 2t;
+//      whatever is still open when the run ends goes to carry slot 2t+1.
+// The fix-up pass adds the carry partials of each row in slot (= entry) order.  Rows written
+// directly and rows completed by the fix-up are disjoint, so there are no atomics on y and the
+// result is deterministic.
+// Summation order: inside a group a Hillis-Steele tree; groups of one row are chained left to
+// right (open + group); run partials are added left to right by the fix-up.
+static constexpr int kMergeRun = 1024;  // entries per warp-run
+
+template <typename V>
+__global__ void __launch_bounds__(256) csr_merge_kernel(int nrow, int nnz, const int* __restrict__ row_ptr,
+                                                        const int* __restrict__ col, const V* __restrict__ val,
+                                                        const V* __restrict__ x, V* __restrict__ y,
+                                                        int* __restrict__ carry_row, V* __restrict__ carry_val, int nruns)
+{
+    __shared__ int mark_all[8][kMergeRun];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int run = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (run >= nruns) return;  // warp-uniform; no CTA-wide barriers below
+    int* mark = mark_all[threadIdx.x >> 5];
+    const int e0 = run * kMergeRun;
+    const int e1 = min(e0 + kMergeRun, nnz);
+
+    int lo = 0, hi = nrow;  // row_ptr[lo] <= e0 < row_ptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(row_ptr + mid) <= e0) lo = mid; else hi = mid;
+    }
+    const int row_lo = lo;
+    const bool first_shared = __ldg(row_ptr + row_lo) < e0;
+
+    for (int i = lane; i < kMergeRun; i += 32) mark[i] = -1;
+    if (lane == 0) carry_row[2 * run] = -1;
+    __syncwarp();
+    for (int rb = row_lo + 1;; rb += 32) {
+        const int r = rb + lane;
+        const int s = (r <= nrow) ? __ldg(row_ptr + r) : 0x7fffffff;
+        if (r < nrow && s < e1) atomicMax(&mark[s - e0], r);
+        if (__any_sync(full, s >= e1)) break;
+    }
+    __syncwarp();
+
+    auto emit = [&](int r, V p) {
+        if (r == row_lo && first_shared) {
+            carry_row[2 * run] = r;
+            carry_val[2 * run] = p;
+        } else {
+            y[r] = add_rn(y[r], p);
+        }
+    };
+
+    int run_row = row_lo;
+    int open_row = -1;
+    V open_sum = V(0);
+    for (int g = e0; g < e1; g += 32) {
+        const int e = g + lane;
+        const bool ok = e < e1;
+        V p = V(0);
+        if (ok) p = mul_rn(ld_stream(val + e), ld_gather(x + ld_stream(col + e)));
+        int m = ok ? mark[e - e0] : -1;
+        if (lane == 0) m = max(m, run_row);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(full, m, d);
+            if (lane >= d) m = max(m, t);
+        }
+        run_row = __shfl_sync(full, m, 31);
+        const int r = ok ? m : -2;
+        const int rl = __shfl_up_sync(full, r, 1);
+        const bool head = (lane == 0) || (rl != r);
+        const unsigned heads = __ballot_sync(full, head);
+        const int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const V q = __shfl_up_sync(full, p, d);
+            if (lane - d >= seg_start) p = add_rn(p, q);
+        }
+        const int r0 = __shfl_sync(full, r, 0);
+        if (open_row >= 0) {
+            if (r0 == open_row) {
+                if (seg_start == 0) p = add_rn(open_sum, p);
+            } else if (lane == 0) {
+                emit(open_row, open_sum);  // that row ended exactly at the group boundary
+            }
+        }
+        const int rn = __shfl_down_sync(full, r, 1);
+        const int last = min(31, e1 - g - 1);
+        if (ok && lane != last && rn != r) emit(r, p);
+        open_row = __shfl_sync(full, r, last);
+        open_sum = __shfl_sync(full, p, last);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        carry_row[2 * run + 1] = open_row;
+        carry_val[2 * run + 1] = open_sum;
+    }
+}
+
+template <typename V>
+__global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry_row, const V* __restrict__ carry_val,
+                                       V* __restrict__ y)
+{
+    // Slots are in entry order, so partials of one row are consecutive (ignoring -1 holes).
+    // One thread per slot; the thread owning the FIRST slot of a row adds the whole chain in order.
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const int r = carry_row[i];
+    if (r < 0) return;
+    int k = i - 1;
+    while (k >= 0 && carry_row[k] < 0) --k;
+    if (k >= 0 && carry_row[k] == r) return;  // not the first slot of this row
+    V acc = y[r];
+    for (int j = i; j < nslots; ++j) {
+        const int rj = carry_row[j];
+        if (rj < 0) continue;
+        if (rj != r) break;
+        acc = add_rn(acc, carry_val[j]);
+    }
+    y[r] = acc;
+}
+
+template <typename V>
+__global__ void zero_kernel(int64_t n, V* __restrict__ y)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = V(0);
+}
+
+template <typename V>
+static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* val, const V* x, V* y, int acc,
+                     cudaStream_t s)
+{
+    if (!acc && nrow > 0) {
+        zero_kernel<V><<<div_up(nrow, 256), 256, 0, s>>>(nrow, y);
+        THSP_LAUNCH_CHECK();
+    }
+    if (nnz <= 0 || nrow <= 0) return 0;
+    const int nruns = div_up(nnz, kMergeRun);
+    int* crow = static_cast<int*>(scratch(sizeof(int) * 2 * (size_t)nruns, 2));
+    V* cval = static_cast<V*>(scratch(sizeof(V) * 2 * (size_t)nruns, 3));
+    if (!crow || !cval) return 1;
+    csr_merge_kernel<V><<<div_up(nruns, 8), 256, 0, s>>>(nrow, nnz, rp, col, val, x, y, crow, cval, nruns);
+    THSP_LAUNCH_CHECK();
+    csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// ========================================================================== PLAN ==========
+__global__ void row_hist_kernel(int nrow, const int* __restrict__ row_ptr, unsigned long long* __restrict__ hist,
+                                int* __restrict__ max_len)
+{
+    __shared__ unsigned int h[32];
+    __shared__ int mx;
+    if (threadIdx.x < 32) h[threadIdx.x] = 0;
+    if (threadIdx.x == 0) mx = 0;
+    __syncthreads();
+    int local_max = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x) {
+        int len = row_ptr[r + 1] - row_ptr[r];
+        int b = len <= 0 ? 0 : 32 - __clz(len);  // len in [2^(b-1), 2^b)
+        atomicAdd(&h[b > 31 ? 31 : b], 1u);
+        local_max = max(local_max, len);
+    }
+    atomicMax(&mx, local_max);
+    __syncthreads();
+    if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+    if (threadIdx.x == 0) atomicMax(max_len, mx);
+}
+
+}  // namespace thsp
+
+using namespace thsp;
+
+struct thsp_csr_plan {
+    int nrow, ncol, nnz, value_bytes;
+    const int* row_ptr;
+    const int* col_ind;
+    const void* val;
+    int kernel, lanes;
+    int64_t hist[32];
+    int max_len;
+    StreamCfg stream_cfg;
+    int ctas;
+};
+
+template <typename V>
+static int dispatch(int kernel, int lanes, const StreamCfg* cfg, int nrow, int ncol, int nnz, const int* rp, const int* col,
+                    const V* val, const V* x, V* y, int acc, cudaStream_t s)
+{
+    (void)ncol;
+    if (nrow <= 0) return 0;
+    switch (kernel) {
+        case THSP_CSR_SCALAR: return run_vector<V>(1, nrow, rp, col, val, x, y, acc, s);
+        case THSP_CSR_VECTOR: return run_vector<V>(lanes, nrow, rp, col, val, x, y, acc, s);
+        case THSP_CSR_STREAM: {
+            StreamCfg c = cfg ? *cfg : default_stream_cfg<V>(nrow, nnz);
+            return run_stream<V>(c, sm_count(), nrow, nnz, rp, col, val, x, y, acc, s);
+        }
+        case THSP_CSR_MERGE: return run_merge<V>(nrow, nnz, rp, col, val, x, y, acc, s);
+    }
+    set_error("unknown CSR kernel id %d", kernel);
+    return 2;
+}
+
+static int lanes_for_mean(double mean)
+{
+    int l = 1;
+    while (l < 32 && l * 2 <= mean) l *= 2;  // largest power of two <= mean row length
+    return l;
+}
+
+// Stateless choice (no histogram available): mean row length only.
+static void choose_stateless(int nrow, int nnz, const void* val, const int* col, int* kernel, int* lanes)
+{
+    double mean = nrow > 0 ? (double)nnz / nrow : 0.0;
+    bool aligned = ((((uintptr_t)val) | ((uintptr_t)col)) & 15) == 0;
+    if (aligned && mean >= 4.0 && mean <= 60.0) {
+        *kernel = THSP_CSR_STREAM;
+        *lanes = 1;
+    } else {
+        *kernel = THSP_CSR_VECTOR;
+        *lanes = lanes_for_mean(mean);
+    }
+}
+
+template <typename V>
+static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s)
+{
+    if (p->nrow <= 0) return 0;
+    if (p->kernel == THSP_CSR_STREAM)
+        return run_stream<V>(p->stream_cfg, p->ctas, p->nrow, p->nnz, p->row_ptr, p->col_ind,
+                             static_cast<const V*>(p->val), x, y, acc, s);
+    return dispatch<V>(p->kernel, p->lanes, &p->stream_cfg, p->nrow, p->ncol, p->nnz, p->row_ptr, p->col_ind,
+                       static_cast<const V*>(p->val), x, y, acc, s);
+}
+
+extern "C" {
+
+int thsp_csr_spmv_kernel_f64(int kernel, int lanes, int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind,
+                             const double* val, const double* x, double* y, int accumulate, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (kernel == THSP_CSR_AUTO) choose_stateless(nrow, nnz, val, col_ind, &kernel, &lanes);
+    return dispatch<double>(kernel, lanes, nullptr, nrow, ncol, nnz, row_ptr, col_ind, val, x, y, accumulate, as_stream(stream));
+}
+int thsp_csr_spmv_kernel_f32(int kernel, int lanes, int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind,
+                             const float* val, const float* x, float* y, int accumulate, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (kernel == THSP_CSR_AUTO) choose_stateless(nrow, nnz, val, col_ind, &kernel, &lanes);
+    return dispatch<float>(kernel, lanes, nullptr, nrow, ncol, nnz, row_ptr, col_ind, val, x, y, accumulate, as_stream(stream));
+}
+int thsp_csr_spmv_f64(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const double* val,
+                      const double* x, double* y, int accumulate, thsp_stream_t stream)
+{
+    return thsp_csr_spmv_kernel_f64(THSP_CSR_AUTO, 0, nrow, ncol, nnz, row_ptr, col_ind, val, x, y, accumulate, stream);
+}
+int thsp_csr_spmv_f32(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const float* val,
+                      const float* x, float* y, int accumulate, thsp_stream_t stream)
+{
+    return thsp_csr_spmv_kernel_f32(THSP_CSR_AUTO, 0, nrow, ncol, nnz, row_ptr, col_ind, val, x, y, accumulate, stream);
+}
+
+int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind,
+                         const void* val, int value_bytes, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    THSP_REQUIRE(value_bytes == 8 || value_bytes == 4, "value_bytes must be 8 or 4");
+    THSP_REQUIRE(nrow >= 0 && nnz >= 0, "negative size");
+    cudaStream_t s = as_stream(stream);
+    thsp_csr_plan* p = new thsp_csr_plan();
+    p->nrow = nrow; p->ncol = ncol; p->nnz = nnz; p->value_bytes = value_bytes;
+    p->row_ptr = row_ptr; p->col_ind = col_ind; p->val = val;
+    p->ctas = sm_count();
+    for (int i = 0; i < 32; ++i) p->hist[i] = 0;
+    p->max_len = 0;
+    if (nrow > 0) {
+        unsigned long long* dh = static_cast<unsigned long long*>(scratch(33 * sizeof(unsigned long long), 4));
+        if (!dh) { delete p; return 1; }
+        int* dmax = reinterpret_cast<int*>(dh + 32);
+        THSP_CUDA(cudaMemsetAsync(dh, 0, 33 * sizeof(unsigned long long), s));
+        row_hist_kernel<<<std::min(div_up(nrow, 256), sm_count() * 8), 256, 0, s>>>(nrow, row_ptr, dh, dmax);
+        THSP_LAUNCH_CHECK();
+        unsigned long long hh[33];
+        THSP_CUDA(cudaMemcpyAsync(hh, dh, sizeof(hh), cudaMemcpyDeviceToHost, s));
+        THSP_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < 32; ++i) p->hist[i] = (int64_t)hh[i];
+        p->max_len = *reinterpret_cast<int*>(&hh[32]);
+    }
+    // ---- kernel choice from the histogram ------------------------------------------------
+    const double mean = nrow > 0 ? (double)nnz / nrow : 0.0;
+    const bool aligned = ((((uintptr_t)val) | ((uintptr_t)col_ind)) & 15) == 0;
+    // rows at least 8x the mean (and >= 256 entries) make a thread- or vector-per-row sweep
+    // wait on a few lanes: go nnz-balanced.
+    const bool skewed = p->max_len >= 256 && (double)p->max_len > 8.0 * std::max(mean, 1.0);
+    if (skewed) {
+        p->kernel = THSP_CSR_MERGE;
+        p->lanes = 1;
+    } else if (aligned && mean >= 4.0 && p->max_len <= 2048) {
+        p->kernel = THSP_CSR_STREAM;
+        p->lanes = 1;
+    } else {
+        p->kernel = THSP_CSR_VECTOR;
+        p->lanes = lanes_for_mean(mean);
+    }
+    p->stream_cfg = value_bytes == 8 ? default_stream_cfg<double>(nrow, nnz) : default_stream_cfg<float>(nrow, nnz);
+    *out = p;
+    return 0;
+}
+
+int thsp_csr_plan_destroy(thsp_csr_plan* plan)
+{
+    delete plan;
+    return 0;
+}
+int thsp_csr_plan_kernel(const thsp_csr_plan* plan, int* kernel, int* lanes)
+{
+    THSP_REQUIRE(plan != nullptr, "null plan");
+    if (kernel) *kernel = plan->kernel;
+    if (lanes) *lanes = plan->lanes;
+    return 0;
+}
+int thsp_csr_plan_set_kernel(thsp_csr_plan* plan, int kernel, int lanes)
+{
+    THSP_REQUIRE(plan != nullptr, "null plan");
+    THSP_REQUIRE(kernel >= THSP_CSR_SCALAR && kernel <= THSP_CSR_MERGE, "bad kernel id");
+    plan->kernel = kernel;
+    plan->lanes = lanes;
+    return 0;
+}
+int thsp_csr_plan_set_stream_config(thsp_csr_plan* plan, int warps, int stages, int chunk, int ctas)
+{
+    THSP_REQUIRE(plan != nullptr, "null plan");
+    if (warps > 0) plan->stream_cfg.warps = warps;
+    if (stages > 0) plan->stream_cfg.stages = stages;
+    if (chunk > 0) plan->stream_cfg.chunk = chunk;
+    if (ctas > 0) plan->ctas = ctas;
+    return 0;
+}
+int thsp_csr_plan_histogram(const thsp_csr_plan* plan, int64_t* histogram32, int* max_row_len)
+{
+    THSP_REQUIRE(plan != nullptr, "null plan");
+    if (histogram32) for (int i = 0; i < 32; ++i) histogram32[i] = plan->hist[i];
+    if (max_row_len) *max_row_len = plan->max_len;
+    return 0;
+}
+
+int thsp_csr_plan_spmv_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate, thsp_stream_t stream)
+{
+    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
+    return plan_spmv<double>(plan, x, y, accumulate, as_stream(stream));
+}
+int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, int accumulate, thsp_stream_t stream)
+{
+    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 4, "plan is null or not fp32");
+    return plan_spmv<float>(plan, x, y, accumulate, as_stream(stream));
+}
+
+int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host, double* x_dev,
+                                double* y_dev, int accumulate, thsp_stream_t stream)
+{
+    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
+    cudaStream_t s = as_stream(stream);
+    THSP_CUDA(cudaMemcpyAsync(x_dev, x_host, sizeof(double) * (size_t)plan->ncol, cudaMemcpyHostToDevice, s));
+    if (accumulate)
+        THSP_CUDA(cudaMemcpyAsync(y_dev, y_host, sizeof(double) * (size_t)plan->nrow, cudaMemcpyHostToDevice, s));
+    if (plan_spmv<double>(plan, x_dev, y_dev, accumulate, s)) return 1;
+    THSP_CUDA(cudaMemcpyAsync(y_host, y_dev, sizeof(double) * (size_t)plan->nrow, cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

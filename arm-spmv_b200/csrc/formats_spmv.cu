@@ -1,0 +1,298 @@
+// formats_spmv.cu -- ELL, COO, CSC and DIA y += A x for sm_100a.
+//
+// Replaces ELLMatrixMatVector (src/mat_vec.cpp:97-121), COOMatirxMatVector (:18-42),
+// CSCMatrixMatVector (:69-95) and DIAMatrixMatVector (:123-146).  All HBM-bound.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace thsp {
+
+// ============================================================================ ELL ==========
+// Column-major slab: slot k of row i lives at [i + k*nrow].  A thread owns R adjacent rows
+// (R=2 for fp64 -> one 128-bit val load + one 64-bit col load per slot; R=4 for fp32 -> one
+// 128-bit load each), so a warp reads 512 B of val per slot in whole lines.  The accumulator
+// starts from y and adds slots in ascending k with unfused mul/add: exactly the reference's
+// order -> bit-identical, padding slots (col 0, 0.0) included.
+// Four slots are in flight per thread (independent loads issued before the dependent adds).
+template <typename V, int R>
+struct EllVec;
+template <>
+struct EllVec<double, 2> {
+    static __device__ __forceinline__ void load(const double* v, const int* c, double (&vv)[2], int (&cc)[2])
+    {
+        double2 a = ld_stream2(v);
+        int2 b = ld_stream2(c);
+        vv[0] = a.x; vv[1] = a.y; cc[0] = b.x; cc[1] = b.y;
+    }
+};
+template <>
+struct EllVec<float, 4> {
+    static __device__ __forceinline__ void load(const float* v, const int* c, float (&vv)[4], int (&cc)[4])
+    {
+        float4 a = ld_stream4(v);
+        int4 b = ld_stream4(c);
+        vv[0] = a.x; vv[1] = a.y; vv[2] = a.z; vv[3] = a.w;
+        cc[0] = b.x; cc[1] = b.y; cc[2] = b.z; cc[3] = b.w;
+    }
+};
+template <typename V>
+struct EllVec<V, 1> {
+    static __device__ __forceinline__ void load(const V* v, const int* c, V (&vv)[1], int (&cc)[1])
+    {
+        vv[0] = ld_stream(v);
+        cc[0] = ld_stream(c);
+    }
+};
+
+template <typename V, int R>
+__global__ void __launch_bounds__(256) ell_kernel(int nrow, int width, const int* __restrict__ col,
+                                                  const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y)
+{
+    const int i = (blockIdx.x * 256 + threadIdx.x) * R;
+    if (i >= nrow) return;  // nrow % R == 0 is guaranteed by the launcher when R > 1
+    V acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = y[i + r];
+    constexpr int U = 4;
+    int k = 0;
+    for (; k + U <= width; k += U) {
+        V vv[U][R];
+        int cc[U][R];
+        V xx[U][R];
+#pragma unroll
+        for (int u = 0; u < U; ++u) EllVec<V, R>::load(val + (size_t)(k + u) * nrow + i, col + (size_t)(k + u) * nrow + i, vv[u], cc[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < R; ++r) xx[u][r] = ld_gather(x + cc[u][r]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = add_rn(acc[r], mul_rn(vv[u][r], xx[u][r]));
+    }
+    for (; k < width; ++k) {
+        V vv[R];
+        int cc[R];
+        EllVec<V, R>::load(val + (size_t)k * nrow + i, col + (size_t)k * nrow + i, vv, cc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = add_rn(acc[r], mul_rn(vv[r], ld_gather(x + cc[r])));
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[i + r] = acc[r];
+}
+
+template <typename V, int R>
+static int launch_ell(int nrow, int width, const int* col, const V* val, const V* x, V* y, cudaStream_t s)
+{
+    ell_kernel<V, R><<<div_up(div_up(nrow, R), 256), 256, 0, s>>>(nrow, width, col, val, x, y);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// ============================================================================ COO ==========
+// One warp sweeps a contiguous run of entries, 32 per step with coalesced row/col/val loads.
+// Products of equal, ADJACENT rows are combined by a segmented warp scan; the segment that is
+// still open at the end of a step is carried into the next step in registers (carry-out), so a
+// row-sorted COO issues one red.global.add.f64 per row and run instead of one per entry.
+// Segments that close are added into y with an atomic, because an unsorted COO may hold the
+// same row anywhere else (the reference uses `omp atomic` for the same reason, :36-39).
+// Order: tree inside a step, steps chained left to right, atomics in arbitrary order - the
+// reference's own order is unspecified under OpenMP.
+static constexpr int kCooRun = 2048;  // entries per warp
+
+__global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict__ row, const int* __restrict__ col,
+                                                  const double* __restrict__ val, const double* __restrict__ x,
+                                                  double* __restrict__ y)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t e0 = run * kCooRun;
+    if (e0 >= nnz) return;
+    const int e1 = (int)min((int64_t)nnz, e0 + kCooRun);
+    int open_row = -1;
+    double open_sum = 0.0;
+    for (int g = (int)e0; g < e1; g += 32) {
+        const int e = g + lane;
+        const bool ok = e < e1;
+        int r = -2;
+        double p = 0.0;
+        if (ok) {
+            r = ld_stream(row + e);
+            p = mul_rn(ld_stream(val + e), ld_gather(x + ld_stream(col + e)));
+        }
+        const int rl = __shfl_up_sync(full, r, 1);
+        const bool head = (lane == 0) || (rl != r);
+        const unsigned heads = __ballot_sync(full, head);
+        const int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double q = __shfl_up_sync(full, p, d);
+            if (lane - d >= seg_start) p = add_rn(p, q);
+        }
+        const int r0 = __shfl_sync(full, r, 0);
+        if (open_row >= 0) {
+            if (r0 == open_row) {
+                if (seg_start == 0) p = add_rn(open_sum, p);
+            } else if (lane == 0) {
+                atomicAdd(y + open_row, open_sum);
+            }
+        }
+        const int rn = __shfl_down_sync(full, r, 1);
+        const int last = min(31, e1 - g - 1);
+        if (ok && lane != last && rn != r) atomicAdd(y + r, p);
+        open_row = __shfl_sync(full, r, last);
+        open_sum = __shfl_sync(full, p, last);
+    }
+    if (lane == 0 && open_row >= 0) atomicAdd(y + open_row, open_sum);
+}
+
+// ============================================================================ CSC ==========
+// Column scatter with shared-memory-staged partial sums.  A CTA owns kCscCols consecutive
+// columns, i.e. one contiguous run of (row_ind, val) entries, which it streams with coalesced
+// loads.  The column of each entry comes from a binary search in the CTA's slice of col_ptr
+// (kept in shared memory).  Partial sums for rows inside a dense window of kCscWin rows centred
+// on the CTA's columns (where banded / stencil matrices put most of their entries) are
+// accumulated with shared-memory atomics and flushed once with one global atomic per touched
+// row; rows outside the window go straight to global atomics.
+// Order: unspecified (atomics), like the reference's `omp atomic` scatter (:88-91).
+static constexpr int kCscCols = 256;
+static constexpr int kCscWin = 2048;
+
+__global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, const int* __restrict__ col_ptr,
+                                                  const int* __restrict__ row, const double* __restrict__ val,
+                                                  const double* __restrict__ x, double* __restrict__ y)
+{
+    __shared__ int s_cp[kCscCols + 1];
+    __shared__ double s_win[kCscWin];
+    const int c0 = blockIdx.x * kCscCols;
+    const int nc = min(kCscCols, ncol - c0);
+    for (int i = threadIdx.x; i <= nc; i += 256) s_cp[i] = __ldg(col_ptr + c0 + i);
+    for (int i = threadIdx.x; i < kCscWin; i += 256) s_win[i] = 0.0;
+    __syncthreads();
+    const int e0 = s_cp[0], e1 = s_cp[nc];
+    // window of rows around the diagonal block of these columns
+    int w0 = c0 + nc / 2 - kCscWin / 2;
+    w0 = max(0, min(w0, nrow - kCscWin));
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+        int lo = 0, hi = nc;  // s_cp[lo] <= e < s_cp[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_cp[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int r = ld_stream(row + e);
+        const double p = mul_rn(ld_stream(val + e), ld_gather(x + c0 + lo));
+        const int w = r - w0;
+        if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
+        else atomicAdd(y + r, p);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCscWin; i += 256) {
+        const double v = s_win[i];
+        if (v != 0.0 && w0 + i < nrow) atomicAdd(y + w0 + i, v);
+    }
+}
+
+// ============================================================================ DIA ==========
+// Row-major values[i*ndiags + d].  A CTA stages the contiguous block of 128 rows x ndiags
+// values through shared memory with coalesced loads (when it fits), then each thread walks its
+// row's diagonals in ascending d, accumulating into y with unfused mul/add: the reference's
+// order, including its `j < nrow` guard (:140).
+static constexpr int kDiaRows = 128;
+
+__global__ void __launch_bounds__(kDiaRows) dia_kernel(int nrow, int ndiags, const int* __restrict__ off,
+                                                       const double* __restrict__ values, const double* __restrict__ x,
+                                                       double* __restrict__ y, int staged)
+{
+    extern __shared__ double s_v[];
+    const int r0 = blockIdx.x * kDiaRows;
+    const int nr = min(kDiaRows, nrow - r0);
+    const int i = r0 + threadIdx.x;
+    if (staged) {
+        const size_t base = (size_t)r0 * ndiags;
+        const int total = nr * ndiags;
+        for (int t = threadIdx.x; t < total; t += kDiaRows) s_v[t + t / 32] = ld_stream(values + base + t);
+        __syncthreads();
+    }
+    if (i >= nrow) return;
+    double acc = y[i];
+    for (int d = 0; d < ndiags; ++d) {
+        const int j = i + __ldg(off + d);
+        if (j >= 0 && j < nrow) {
+            const int t = threadIdx.x * ndiags + d;
+            const double v = staged ? s_v[t + t / 32] : __ldg(values + (size_t)i * ndiags + d);
+            acc = add_rn(acc, mul_rn(v, ld_gather(x + j)));
+        }
+    }
+    y[i] = acc;
+}
+
+}  // namespace thsp
+
+using namespace thsp;
+
+extern "C" {
+
+int thsp_ell_spmv_f64(int nrow, int ncol, int width, const int* col_ind, const double* val, const double* x, double* y,
+                      thsp_stream_t stream)
+{
+    (void)ncol;
+    if (ensure_device()) return 1;
+    if (nrow <= 0 || width <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const bool vec = (nrow % 2 == 0) && ((((uintptr_t)val) & 15) == 0) && ((((uintptr_t)col_ind) & 7) == 0);
+    return vec ? launch_ell<double, 2>(nrow, width, col_ind, val, x, y, s)
+               : launch_ell<double, 1>(nrow, width, col_ind, val, x, y, s);
+}
+int thsp_ell_spmv_f32(int nrow, int ncol, int width, const int* col_ind, const float* val, const float* x, float* y,
+                      thsp_stream_t stream)
+{
+    (void)ncol;
+    if (ensure_device()) return 1;
+    if (nrow <= 0 || width <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const bool vec = (nrow % 4 == 0) && ((((uintptr_t)val) & 15) == 0) && ((((uintptr_t)col_ind) & 15) == 0);
+    return vec ? launch_ell<float, 4>(nrow, width, col_ind, val, x, y, s)
+               : launch_ell<float, 1>(nrow, width, col_ind, val, x, y, s);
+}
+
+int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                      const double* x, double* y, thsp_stream_t stream)
+{
+    (void)nrow; (void)ncol;
+    if (ensure_device()) return 1;
+    if (nnz <= 0) return 0;
+    const int runs = div_up(nnz, kCooRun);
+    coo_kernel<<<div_up(runs, 8), 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int* row_ind, const double* val,
+                      const double* x, double* y, thsp_stream_t stream)
+{
+    (void)nnz;
+    if (ensure_device()) return 1;
+    if (ncol <= 0 || nrow <= 0) return 0;
+    csc_kernel<<<div_up(ncol, kCscCols), 256, 0, as_stream(stream)>>>(nrow, ncol, col_ptr, row_ind, val, x, y);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_dia_spmv_f64(int nrow, int ncol, int ndiags, const int* offsets, const double* values, const double* x,
+                      double* y, thsp_stream_t stream)
+{
+    (void)ncol;
+    if (ensure_device()) return 1;
+    if (nrow <= 0 || ndiags <= 0) return 0;
+    const size_t words = (size_t)kDiaRows * ndiags;
+    const size_t smem = (words + words / 32 + 1) * sizeof(double);
+    const int staged = smem <= 48 * 1024 ? 1 : 0;
+    dia_kernel<<<div_up(nrow, kDiaRows), kDiaRows, staged ? smem : 0, as_stream(stream)>>>(nrow, ndiags, offsets, values,
+                                                                                          x, y, staged);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

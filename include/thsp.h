@@ -1,0 +1,221 @@
+/*
+ * thsp.h -- C ABI of the B200-native SpMV library (libthsparse_cuda.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The
+ * reference (ChuheHong/arm-spmv) has no FFI of its own -- its API is C++ free functions and
+ * classes (include/mat_vec.h, matrix.h, vec_vec.h, vector.h) -- so each entry point below
+ * names the reference function or loop it replaces (paths relative to the reference root).
+ * The C++ classes in this directory (matrix.h, vector.h, mat_vec.h, vec_vec.h, data_io.h)
+ * are thin g++-compiled callers of these functions; tests/ and bench.py bind the same
+ * functions through ctypes.
+ *
+ * Conventions
+ *  - Every array argument is a DEVICE-accessible pointer (cudaMalloc, cudaMallocManaged or a
+ *    torch CUDA tensor's data_ptr) unless the name ends in _host.
+ *  - Indices are int32, values fp64 unless suffixed _f32 (the reference is double-only;
+ *    fp32 is an extension asked for by the north star).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous on that stream unless documented otherwise; the C++ classes synchronise
+ *    before returning because the reference's API is synchronous (main.cpp:56-59 brackets
+ *    calls with mytimer()).
+ *  - Return value: 0 on success, non-zero on failure; thsp_last_error() describes the last
+ *    failure on the calling thread.  There is no CPU fallback anywhere: without a CUDA device
+ *    every compute entry point fails.
+ */
+#ifndef THSP_H
+#define THSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define THSP_API __attribute__((visibility("default")))
+#else
+#define THSP_API
+#endif
+
+typedef void* thsp_stream_t;
+
+/* ------------------------------------------------------------------ runtime -------- */
+THSP_API const char* thsp_version(void);
+THSP_API const char* thsp_last_error(void);
+THSP_API int thsp_device_count(int* count);
+THSP_API int thsp_set_device(int device);
+THSP_API int thsp_get_device(int* device);
+THSP_API int thsp_sm_count(int* count);
+/* Memory.  `managed` allocations are host-dereferenceable (the reference's classes expose raw
+ * pointers that main.cpp:48-51 reads on the host); see INTEGRATION.md "ownership". */
+THSP_API int thsp_malloc(void** ptr, size_t bytes);
+THSP_API int thsp_malloc_managed(void** ptr, size_t bytes);
+THSP_API int thsp_malloc_host(void** ptr, size_t bytes); /* pinned */
+THSP_API int thsp_free(void* ptr);
+THSP_API int thsp_free_host(void* ptr);
+/* 0 = plain host (or unknown), 1 = device, 2 = managed, 3 = pinned host */
+THSP_API int thsp_pointer_kind(const void* ptr);
+THSP_API int thsp_memcpy_h2d(void* dst, const void* src_host, size_t bytes, thsp_stream_t stream);
+THSP_API int thsp_memcpy_d2h(void* dst_host, const void* src, size_t bytes, thsp_stream_t stream);
+THSP_API int thsp_memcpy_d2d(void* dst, const void* src, size_t bytes, thsp_stream_t stream);
+THSP_API int thsp_memset(void* dst, int byte, size_t bytes, thsp_stream_t stream);
+THSP_API int thsp_prefetch(const void* managed_ptr, size_t bytes, int to_device, thsp_stream_t stream);
+THSP_API int thsp_stream_sync(thsp_stream_t stream);
+THSP_API int thsp_device_sync(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+THSP_API uint64_t thsp_launch_count(void);
+
+/* --------------------------------------------------------------------- SpMV -------- */
+/* Kernel ids for CSR.  AUTO picks from the row-length statistics gathered by the plan. */
+enum {
+    THSP_CSR_AUTO = 0,
+    THSP_CSR_SCALAR = 1,    /* one thread per row, loads straight from global              */
+    THSP_CSR_VECTOR = 2,    /* L lanes per row (L = 2..32, `lanes` argument), shuffle tree   */
+    THSP_CSR_STREAM = 3,    /* TMA bulk ring -> shared memory, one thread per row, in order  */
+    THSP_CSR_MERGE = 4      /* nnz-balanced tiles with segmented reduction + carry fix-up    */
+};
+
+/* CSRMatrixMatVector (src/mat_vec.cpp:44-67): y[i] (+)= sum_j val[j]*x[col[j]].
+ * accumulate=1 is the reference's y += A x; accumulate=0 writes y = A x (saves the y read and
+ * the caller's Fill(0)).  Stateless form: chooses a kernel from nnz/nrow alone. */
+THSP_API int thsp_csr_spmv_f64(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const double* val,
+                               const double* x, double* y, int accumulate, thsp_stream_t stream);
+THSP_API int thsp_csr_spmv_f32(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const float* val,
+                               const float* x, float* y, int accumulate, thsp_stream_t stream);
+/* Forced-kernel form (tests and tuning).  `lanes` is used by THSP_CSR_VECTOR only. */
+THSP_API int thsp_csr_spmv_kernel_f64(int kernel, int lanes, int nrow, int ncol, int nnz, const int* row_ptr,
+                                      const int* col_ind, const double* val, const double* x, double* y,
+                                      int accumulate, thsp_stream_t stream);
+THSP_API int thsp_csr_spmv_kernel_f32(int kernel, int lanes, int nrow, int ncol, int nnz, const int* row_ptr,
+                                      const int* col_ind, const float* val, const float* x, float* y,
+                                      int accumulate, thsp_stream_t stream);
+
+/* Plan: row-length histogram -> kernel + lane count, plus the merge kernel's tile table.
+ * Replaces nothing in the reference (its loop is static-scheduled, src/mat_vec.cpp:54-57);
+ * it is where the north star's "lane count picked from the row-length histogram" lives. */
+typedef struct thsp_csr_plan thsp_csr_plan;
+THSP_API int thsp_csr_plan_create(thsp_csr_plan** plan, int nrow, int ncol, int nnz, const int* row_ptr,
+                                  const int* col_ind, const void* val, int value_bytes /* 8 or 4 */,
+                                  thsp_stream_t stream);
+THSP_API int thsp_csr_plan_destroy(thsp_csr_plan* plan);
+THSP_API int thsp_csr_plan_kernel(const thsp_csr_plan* plan, int* kernel, int* lanes);
+THSP_API int thsp_csr_plan_set_kernel(thsp_csr_plan* plan, int kernel, int lanes);
+/* Tuning knobs of the STREAM kernel (0 keeps the current value): warps per CTA, ring depth per
+ * warp, entries per stage (multiple of 4), number of persistent CTAs. */
+THSP_API int thsp_csr_plan_set_stream_config(thsp_csr_plan* plan, int warps, int stages, int chunk, int ctas);
+/* histogram[b] = number of rows whose length l satisfies: b=0: l==0; b>=1: 2^(b-1) <= l < 2^b  (32 bins) */
+THSP_API int thsp_csr_plan_histogram(const thsp_csr_plan* plan, int64_t* histogram32, int* max_row_len);
+THSP_API int thsp_csr_plan_spmv_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate,
+                                    thsp_stream_t stream);
+THSP_API int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, int accumulate,
+                                    thsp_stream_t stream);
+/* Same, with HOST x and y (pinned or pageable): H2D of x, kernel, D2H of y, then synchronises.
+ * This is the call bench.py times for its end-to-end number. */
+THSP_API int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host,
+                                         double* x_dev_scratch, double* y_dev_scratch, int accumulate,
+                                         thsp_stream_t stream);
+
+/* ELLMatrixMatVector (src/mat_vec.cpp:97-121): column-major slab col[i + k*nrow]; accumulates
+ * slot by slot into y exactly in the reference's order (y's old value is the first addend). */
+THSP_API int thsp_ell_spmv_f64(int nrow, int ncol, int width, const int* col_ind, const double* val, const double* x,
+                               double* y, thsp_stream_t stream);
+THSP_API int thsp_ell_spmv_f32(int nrow, int ncol, int width, const int* col_ind, const float* val, const float* x,
+                               float* y, thsp_stream_t stream);
+/* COOMatirxMatVector [sic] (src/mat_vec.cpp:18-42): y[row[k]] += val[k]*x[col[k]]. */
+THSP_API int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                               const double* x, double* y, thsp_stream_t stream);
+/* CSCMatrixMatVector (src/mat_vec.cpp:69-95): column scatter y[row[j]] += val[j]*x[c]. */
+THSP_API int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int* row_ind, const double* val,
+                               const double* x, double* y, thsp_stream_t stream);
+/* DIAMatrixMatVector (src/mat_vec.cpp:123-146): row-major values[i*ndiags+d], guard j<nrow. */
+THSP_API int thsp_dia_spmv_f64(int nrow, int ncol, int ndiags, const int* offsets, const double* values,
+                               const double* x, double* y, thsp_stream_t stream);
+
+/* -------------------------------------------------------------- conversions -------- */
+/* All are stable: within a row (column) entries keep their COO order and duplicates are kept,
+ * so every output array equals the reference constructor's bit for bit. */
+/* CSRMatrix::CSRMatrix(const COOMatrix&) (src/matrix.cpp:115-154).  diagonal may be NULL;
+ * *ndiag (host, may be NULL) receives the number of row==col entries; at most nrow are stored. */
+THSP_API int thsp_coo2csr(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                          int* row_ptr, int* out_col_ind, double* out_val, double* diagonal, int* ndiag,
+                          thsp_stream_t stream);
+/* CSCMatrix::CSCMatrix(const COOMatrix&) (src/matrix.cpp:295-325). */
+THSP_API int thsp_coo2csc(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                          int* col_ptr, int* out_row_ind, double* out_val, thsp_stream_t stream);
+/* ELLMatrix::ELLMatrix(const COOMatrix&) (src/matrix.cpp:450-500) in two steps because the
+ * caller must allocate nrow*width slots: width = longest row, then the fill. Synchronous. */
+THSP_API int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_stream_t stream);
+THSP_API int thsp_coo2ell(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                          int width, int* out_col_ind, double* out_val, double* diagonal, int* ndiag,
+                          thsp_stream_t stream);
+/* DIAMatrix::DIAMatrix(const CSRMatrix&) (src/matrix.cpp:673-726): count/emit ascending offsets,
+ * then the row-major fill (last duplicate wins).  offsets == NULL just counts. Synchronous. */
+THSP_API int thsp_csr2dia_offsets(int nrow, int ncol, const int* row_ptr, const int* col_ind, int* ndiags,
+                                  int* offsets, int offsets_capacity, thsp_stream_t stream);
+THSP_API int thsp_csr2dia_fill(int nrow, int ncol, const int* row_ptr, const int* col_ind, const double* val,
+                               int ndiags, const int* offsets, double* values, thsp_stream_t stream);
+/* row_ptr scan on its own: exclusive prefix sum of n int32 counts into out[0..n] (out[n]=total). */
+THSP_API int thsp_exclusive_scan_i32(int n, const int* counts, int* out, thsp_stream_t stream);
+
+/* ------------------------------------------------------------------ vectors -------- */
+/* vec_dot (src/vec_vec.cpp:15-29).  Deterministic two-level tree; *result_host is written
+ * after a stream synchronise.  The _dev form leaves the scalar on the device (no sync). */
+THSP_API int thsp_dot_f64(int64_t n, const double* x, const double* y, double* result_host, thsp_stream_t stream);
+THSP_API int thsp_dot_dev_f64(int64_t n, const double* x, const double* y, double* result_dev, thsp_stream_t stream);
+/* vec_axpby (src/vec_vec.cpp:31-94): same seven branches, unfused multiply/add -> bit-exact. */
+THSP_API int thsp_axpby_f64(int64_t n, double alpha, const double* x, double beta, const double* y, double* w,
+                            thsp_stream_t stream);
+/* Vector::Fill/Scale/Shift/Copy/AddScaled/Add2Scaled (src/vector.cpp:59-159), bit-exact. */
+THSP_API int thsp_fill_f64(int64_t n, double a, double* v, thsp_stream_t stream);
+THSP_API int thsp_scale_f64(int64_t n, double a, double* v, thsp_stream_t stream);
+THSP_API int thsp_shift_f64(int64_t n, double a, double* v, thsp_stream_t stream);
+THSP_API int thsp_copy_f64(int64_t n, const double* x, double* v, thsp_stream_t stream);
+THSP_API int thsp_add_scaled_f64(int64_t n, double a, const double* x, double* v, thsp_stream_t stream);
+THSP_API int thsp_add2_scaled_f64(int64_t n, double a, const double* x, double b, const double* y, double* v,
+                                  thsp_stream_t stream);
+/* checkVector (src/vector.cpp:161-171): *ok_host = 1 iff sizes match and max|x-y| <= 1e-6. Synchronous. */
+THSP_API int thsp_check_vector_f64(int64_t nx, const double* x, int64_t ny, const double* y, int* ok_host,
+                                   thsp_stream_t stream);
+
+/* --------------------------------------------- row-block partition (multi-GPU) ------ */
+/* *MatVectorNuma (src/mat_vec.cpp:230-268): equal row blocks, last takes the remainder. Host-only. */
+THSP_API int thsp_partition_rows(int64_t nrow, int nparts, int part, int64_t* start, int64_t* count);
+/* sub_row_ptr[j] = row_ptr[start+j] - row_ptr[start], j = 0..count (src/mat_vec.cpp:260-263). */
+THSP_API int thsp_csr_slice_row_ptr(const int* row_ptr, int start, int count, int* sub_row_ptr, thsp_stream_t stream);
+/* Power-iteration tail fused with the x refresh: dst_k[offset+i] = src[i] * (1/sqrt(*sumsq_dev))
+ * for every peer replica k (peer pointers are device pointers mapped over NVLink, or just the
+ * local replica when npeers == 1).  Replaces nothing in the reference (its NUMA loop never
+ * refreshes x); composes vec_axpby's beta==0 branch (src/vec_vec.cpp:46-53). */
+THSP_API int thsp_scale_broadcast_f64(int64_t n, const double* src, const double* sumsq_dev, double* const* peer_dst,
+                                      int npeers, int64_t offset, thsp_stream_t stream);
+/* sum of squares of y into *out_dev (device scalar), deterministic; = vec_dot(y,y). */
+THSP_API int thsp_sumsq_dev_f64(int64_t n, const double* y, double* out_dev, thsp_stream_t stream);
+
+/* --------------------------------------------------------- synthetic inputs --------- */
+/* SURVEY.md 8(d).  Device-side generators (the big configs cannot go through a .mtx file);
+ * oracle/oracle.c carries CPU twins that produce identical arrays. */
+/* 27-point stencil on n^3, rows [row_begin,row_end), row_ptr rebased to 0.  Call with
+ * col_ind == NULL to fill row_ptr only (sub_nnz = row_ptr[row_end-row_begin] fits int32). */
+THSP_API int thsp_gen_stencil27_csr(int n, int64_t row_begin, int64_t row_end, int* row_ptr, int* col_ind,
+                                    double* val, thsp_stream_t stream);
+THSP_API int64_t thsp_stencil27_nnz(int n, int64_t row_begin, int64_t row_end);
+/* Same matrix straight into the reference's column-major ELL slab (width 27). */
+THSP_API int thsp_gen_stencil27_ell(int n, int* col_ind, double* val, thsp_stream_t stream);
+/* Same matrix as COO in row-major order (for the conversion benchmarks). */
+THSP_API int thsp_gen_stencil27_coo(int n, int* row_ind, int* col_ind, double* val, thsp_stream_t stream);
+THSP_API int thsp_gen_lap5_coo(int n, int* row_ind, int* col_ind, double* val, thsp_stream_t stream);
+THSP_API int64_t thsp_lap5_nnz(int n);
+THSP_API int thsp_gen_uniform_coo(int nrow, int ncol, int64_t nnz, uint64_t seed, int* row_ind, int* col_ind,
+                                  double* val, thsp_stream_t stream);
+THSP_API int thsp_gen_rmat_coo(int scale, int64_t nnz, uint64_t seed, int* row_ind, int* col_ind, double* val,
+                               thsp_stream_t stream);
+THSP_API int thsp_gen_vector_f64(int64_t n, uint64_t seed, double* v, thsp_stream_t stream);
+THSP_API int thsp_f64_to_f32(int64_t n, const double* src, float* dst, thsp_stream_t stream);
+/* Write `bytes` of junk through a buffer larger than L2 so the next timed launch starts cold. */
+THSP_API int thsp_flush_l2(void* scratch, size_t bytes, thsp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THSP_H */

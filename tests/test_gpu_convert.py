@@ -1,0 +1,114 @@
+"""-m gpu: format conversions on the GPU are bit-identical to the reference constructors."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from conftest import load_golden
+from gpu_util import assert_bits, dev, host
+
+pytestmark = pytest.mark.gpu
+NAMES = list(C.cases().keys())
+
+
+def convert_all(H, nrow, ncol, ri, ci, va):
+    A = H.COOMatrix(nrow, ncol, ri, ci, va)
+    B = H.CSRMatrix(A); Cc = H.CSCMatrix(A); D = H.ELLMatrix(A)
+    return A, B, Cc, D
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_conversions_match_golden(thsp, cuda, name):
+    from arm_spmv_b200 import host as H
+    g = load_golden(name)
+    nrow, ncol = int(g["nrow"]), int(g["ncol"])
+    A, B, Cc, D = convert_all(H, nrow, ncol, g["ri"], g["ci"], g["va"])
+    assert_bits(host(B.row_ptr), g["csr_row_ptr"], "row_ptr"); assert_bits(host(B.col_ind), g["csr_col_ind"], "csr col")
+    assert_bits(host(B.values), g["csr_values"], "csr val")
+    assert B.ndiag == len(g["csr_diagonal"]); assert_bits(host(B.diagonal)[:B.ndiag], g["csr_diagonal"], "diag")
+    assert_bits(host(Cc.col_ptr), g["csc_col_ptr"], "col_ptr"); assert_bits(host(Cc.row_ind), g["csc_row_ind"], "csc row")
+    assert_bits(host(Cc.values), g["csc_values"], "csc val")
+    assert D.nonzeros_in_row == int(g["ell_width"])
+    assert_bits(host(D.col_ind), g["ell_col_ind"], "ell col"); assert_bits(host(D.values), g["ell_values"], "ell val")
+    assert_bits(host(D.diagonal)[:D.ndiag], g["ell_diagonal"], "ell diag")
+    if "dia_offsets" in g:
+        E = H.DIAMatrix(B)
+        assert E.ndiags == len(g["dia_offsets"])
+        assert_bits(host(E.offsets), g["dia_offsets"], "dia off"); assert_bits(host(E.values), g["dia_values"], "dia val")
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rmat", "lap5_sorted", "stencil_shuffled"])
+def test_conversions_match_oracle_medium(thsp, cuda, oracle, kind):
+    """Sizes that exercise several radix passes, many CTAs and the multi-level scan."""
+    from arm_spmv_b200 import host as H
+    if kind == "uniform":
+        nrow, ncol = 70001, 65537
+        ri, ci, va = oracle.gen_uniform_coo(nrow, ncol, 1_200_003, 43)
+    elif kind == "rmat":
+        nrow = ncol = 1 << 17
+        ri, ci, va = oracle.gen_rmat_coo(17, 1_500_000, 42)
+    elif kind == "lap5_sorted":
+        nrow = ncol = 300 * 300
+        ri, ci, va = oracle.gen_lap5_coo(300)
+    else:
+        rp, cc, vv = oracle.gen_stencil27_csr(40)
+        nrow = ncol = 64000
+        ri = np.repeat(np.arange(nrow, dtype=np.int32), np.diff(rp))
+        p = np.random.RandomState(2).permutation(len(vv))
+        ri, ci, va = ri[p], cc[p], vv[p]
+    if kind == "rmat":   # the ELL slab of a power-law matrix is huge: CSR/CSC only
+        A = H.COOMatrix(nrow, ncol, ri, ci, va); B = H.CSRMatrix(A); Cc = H.CSCMatrix(A); D = None
+    else:
+        A, B, Cc, D = convert_all(H, nrow, ncol, ri, ci, va)
+    rp, co, cv, dg = oracle.coo2csr(nrow, ncol, ri, ci, va)
+    assert_bits(host(B.row_ptr), rp, "row_ptr"); assert_bits(host(B.col_ind), co, "csr col"); assert_bits(host(B.values), cv, "csr val")
+    assert B.ndiag == len(dg); assert_bits(host(B.diagonal)[:B.ndiag], dg, "diag")
+    cp, ro, cv2 = oracle.coo2csc(nrow, ncol, ri, ci, va)
+    assert_bits(host(Cc.col_ptr), cp, "col_ptr"); assert_bits(host(Cc.row_ind), ro, "csc row"); assert_bits(host(Cc.values), cv2, "csc val")
+    if D is not None:
+        k, eco, eva, edg = oracle.coo2ell(nrow, ncol, ri, ci, va)
+        assert D.nonzeros_in_row == k
+        assert_bits(host(D.col_ind), eco, "ell col"); assert_bits(host(D.values), eva, "ell val")
+    if kind == "lap5_sorted":
+        E = H.DIAMatrix(B); off, dv = oracle.csr2dia(nrow, ncol, rp, co, cv)
+        assert_bits(host(E.offsets), off, "dia off"); assert_bits(host(E.values), dv, "dia val")
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 1023, 1024, 1025, 5000, 1024 * 1024 + 17, 3_000_001])
+def test_exclusive_scan(thsp, cuda, n):
+    rs = np.random.RandomState(n % 97)
+    a = rs.randint(0, 50, n).astype(np.int32)
+    d = dev(np.concatenate([a, [0]]).astype(np.int32))
+    out = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    thsp.lib.check(thsp.load().thsp_exclusive_scan_i32(n, thsp.lib.ptr(d), thsp.lib.ptr(out), thsp.lib.current_stream()))
+    want = np.concatenate([[0], np.cumsum(a)]).astype(np.int32)
+    assert_bits(host(out), want, f"scan {n}")
+    # in place (the way row_ptr is built)
+    thsp.lib.check(thsp.load().thsp_exclusive_scan_i32(n, thsp.lib.ptr(d), thsp.lib.ptr(d), thsp.lib.current_stream()))
+    assert_bits(host(d), want, f"scan in place {n}")
+
+
+def test_generators_match_cpu_twins(thsp, cuda, oracle):
+    from arm_spmv_b200 import host as H
+    A = H.stencil27_csr(9)
+    rp, ci, va = oracle.gen_stencil27_csr(9)
+    assert_bits(host(A.row_ptr), rp, "st rp"); assert_bits(host(A.col_ind), ci, "st ci"); assert_bits(host(A.values), va, "st va")
+    S = H.stencil27_csr(9, 100, 517)
+    rp2, ci2, va2 = oracle.gen_stencil27_csr(9, 100, 517)
+    assert_bits(host(S.row_ptr), rp2, "slab rp"); assert_bits(host(S.col_ind), ci2, "slab ci")
+    E = H.stencil27_ell(9)
+    ri = np.repeat(np.arange(729, dtype=np.int32), np.diff(rp))
+    k, eco, eva, _ = oracle.coo2ell(729, 729, ri, ci, va)
+    assert k == 27
+    assert_bits(host(E.col_ind), eco, "ell gen col"); assert_bits(host(E.values), eva, "ell gen val")
+    Cq = H.stencil27_coo(9)
+    assert_bits(host(Cq.row_ind), ri, "coo gen row"); assert_bits(host(Cq.col_ind), ci, "coo gen col")
+    Lp = H.lap5_coo(33); lri, lci, lva = oracle.gen_lap5_coo(33)
+    assert_bits(host(Lp.row_ind), lri, "lap ri"); assert_bits(host(Lp.col_ind), lci, "lap ci"); assert_bits(host(Lp.values), lva, "lap va")
+    U = H.uniform_coo(5000, 4000, 100003, 43); uri, uci, uva = oracle.gen_uniform_coo(5000, 4000, 100003, 43)
+    assert_bits(host(U.row_ind), uri, "uni ri"); assert_bits(host(U.col_ind), uci, "uni ci"); assert_bits(host(U.values), uva, "uni va")
+    Rm = H.rmat_coo(14, 50000, 42); rri, rci, rva = oracle.gen_rmat_coo(14, 50000, 42)
+    assert_bits(host(Rm.row_ind), rri, "rmat ri"); assert_bits(host(Rm.col_ind), rci, "rmat ci"); assert_bits(host(Rm.values), rva, "rmat va")
+    assert_bits(host(H.gen_vector(10007, 5).values), oracle.gen_vector(10007, 5), "vec")

@@ -1,0 +1,203 @@
+"""-m gpu parity: every SpMV kernel (through the C ABI) against the CPU oracle and the golden
+fixtures generated from the unmodified reference.
+
+Tolerances (north star): fp64 per-row error <= 1e-12, fp32 <= 1e-5, where the per-row error is
+|y - y_ref| / (sum_j |a_ij x_j| + |y0|).  Kernels that keep the reference's
+summation order (CSR scalar/stream, ELL, DIA) must be BIT-IDENTICAL to it."""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from conftest import load_golden
+from gpu_util import assert_bits, dev, host, max_row_error, row_scale_coo, row_scale_csr
+
+pytestmark = pytest.mark.gpu
+TOL64 = 1e-12
+TOL32 = 1e-5
+NAMES = list(C.cases().keys())
+SCALAR, VECTOR, STREAM, MERGE = 1, 2, 3, 4
+CSR_KERNELS = [(SCALAR, 1), (VECTOR, 2), (VECTOR, 4), (VECTOR, 8), (VECTOR, 16), (VECTOR, 32), (STREAM, 1), (MERGE, 1)]
+EXACT = {(SCALAR, 1), (STREAM, 1)}
+
+
+def run_csr(thsp, kernel, lanes, nrow, ncol, rp, ci, va, x, y0, accumulate=True, dtype=torch.float64):
+    from arm_spmv_b200 import host as H
+    A = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=dev(rp), col_ind=dev(ci), values=dev(va, dtype))
+    xd, yd = dev(x, dtype), dev(y0, dtype)
+    H.csr_spmv_kernel(kernel, lanes, A, xd, yd, accumulate)
+    return host(yd)
+
+
+def synthetic(oracle, which):
+    if which == "stencil12":
+        rp, ci, va = oracle.gen_stencil27_csr(12)
+        return 1728, 1728, rp, ci, va
+    if which == "lap5_40":
+        ri, cj, v = oracle.gen_lap5_coo(40)
+        rp, ci, va, _ = oracle.coo2csr(1600, 1600, ri, cj, v)
+        return 1600, 1600, rp, ci, va
+    if which == "rmat12":
+        ri, cj, v = oracle.gen_rmat_coo(12, 60000, 42)
+        rp, ci, va, _ = oracle.coo2csr(4096, 4096, ri, cj, v)
+        return 4096, 4096, rp, ci, va
+    if which == "uniform":
+        ri, cj, v = oracle.gen_uniform_coo(3000, 2500, 20011, 43)
+        rp, ci, va, _ = oracle.coo2csr(3000, 2500, ri, cj, v)
+        return 3000, 2500, rp, ci, va
+    if which == "hub":  # one row holding 70% of a 200k-entry matrix: runs far longer than a merge tile
+        rs = np.random.RandomState(5)
+        nrow = ncol = 5000
+        ri = rs.randint(0, nrow, 200000).astype(np.int32); ri[:140000] = 1234
+        cj = rs.randint(0, ncol, 200000).astype(np.int32); v = rs.uniform(-1, 1, 200000)
+        rp, ci, va, _ = oracle.coo2csr(nrow, ncol, ri, cj, v)
+        return nrow, ncol, rp, ci, va
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("kernel,lanes", CSR_KERNELS)
+@pytest.mark.parametrize("name", NAMES)
+def test_csr_golden(thsp, cuda, name, kernel, lanes):
+    g = load_golden(name)
+    nrow, ncol = int(g["nrow"]), int(g["ncol"])
+    rp, ci, va, x, y0 = g["csr_row_ptr"], g["csr_col_ind"], g["csr_values"], g["x"], g["y0"]
+    y = run_csr(thsp, kernel, lanes, nrow, ncol, rp, ci, va, x, y0)
+    if (kernel, lanes) in EXACT:
+        assert_bits(y, g["y_csr"], f"csr {name} k{kernel}")
+    else:
+        assert max_row_error(y, g["y_csr"], row_scale_csr(nrow, rp, ci, va, x), y0) <= TOL64
+
+
+@pytest.mark.parametrize("kernel,lanes", CSR_KERNELS)
+@pytest.mark.parametrize("which", ["stencil12", "lap5_40", "rmat12", "uniform", "hub"])
+@pytest.mark.parametrize("accumulate", [True, False])
+def test_csr_synthetic(thsp, cuda, oracle, which, kernel, lanes, accumulate):
+    nrow, ncol, rp, ci, va = synthetic(oracle, which)
+    x = oracle.gen_vector(ncol, 7)
+    y0 = oracle.gen_vector(nrow, 8) - 0.5
+    ref = oracle.csr_spmv(nrow, ncol, rp, ci, va, x, y0 if accumulate else np.zeros(nrow))
+    y = run_csr(thsp, kernel, lanes, nrow, ncol, rp, ci, va, x, y0, accumulate)
+    if (kernel, lanes) in EXACT:
+        assert_bits(y, ref, f"csr {which} k{kernel} acc{accumulate}")
+    else:
+        assert max_row_error(y, ref, row_scale_csr(nrow, rp, ci, va, x), y0 if accumulate else None) <= TOL64
+
+
+def test_csr_stream_ragged_alignment(thsp, cuda, oracle):
+    """Stream kernel: tiles that start at every residue mod 4, nnz not a multiple of 4, rows longer
+    than one shared-memory stage, and sub-array views whose base is only 16 B aligned."""
+    rs = np.random.RandomState(3)
+    for trial in range(6):
+        nrow = int(rs.randint(1, 400)); ncol = int(rs.randint(1, 300))
+        lens = rs.randint(0, 9, nrow)
+        if trial % 2:
+            lens[rs.randint(0, nrow)] = 5000  # several chunks for one tile
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        nnz = int(rp[-1])
+        ci = rs.randint(0, ncol, nnz).astype(np.int32); va = rs.uniform(-1, 1, nnz)
+        x = rs.uniform(0, 1, ncol); y0 = rs.uniform(-1, 1, nrow)
+        y = run_csr(thsp, STREAM, 1, nrow, ncol, rp, ci, va, x, y0)
+        assert_bits(y, oracle.csr_spmv(nrow, ncol, rp, ci, va, x, y0), f"ragged trial {trial}")
+
+
+def test_csr_plan_picks_kernel_from_histogram(thsp, cuda, oracle):
+    from arm_spmv_b200 import host as H
+    nrow, ncol, rp, ci, va = synthetic(oracle, "stencil12")
+    A = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=dev(rp), col_ind=dev(ci), values=dev(va))
+    assert A.plan_kernel()[0] == "stream"
+    nrow, ncol, rp, ci, va = synthetic(oracle, "hub")
+    B = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=dev(rp), col_ind=dev(ci), values=dev(va))
+    assert B.plan_kernel()[0] == "merge"
+    # plan path result == oracle
+    x = H.Vector(oracle.gen_vector(ncol, 1)); y = H.Vector(np.zeros(nrow))
+    H.CSRMatrixMatVector(B, x, y)
+    ref = oracle.csr_spmv(nrow, ncol, rp, ci, va, host(x.values), np.zeros(nrow))
+    assert max_row_error(host(y.values), ref, row_scale_csr(nrow, rp, ci, va, host(x.values))) <= TOL64
+    # histogram bins: 2^(b-1) <= len < 2^b
+    import ctypes
+    hist = (ctypes.c_int64 * 32)(); mx = ctypes.c_int()
+    thsp.lib.check(thsp.load().thsp_csr_plan_histogram(B.plan(), hist, ctypes.byref(mx)))
+    lens = np.diff(rp)
+    assert mx.value == lens.max() and sum(hist) == nrow and hist[0] == int((lens == 0).sum())
+
+
+@pytest.mark.parametrize("kernel,lanes", [(SCALAR, 1), (VECTOR, 8), (STREAM, 1), (MERGE, 1)])
+def test_csr_fp32(thsp, cuda, oracle, kernel, lanes):
+    nrow, ncol, rp, ci, va = synthetic(oracle, "stencil12")
+    x = oracle.gen_vector(ncol, 7).astype(np.float32); va32 = va.astype(np.float32)
+    y0 = np.zeros(nrow, np.float32)
+    y = run_csr(thsp, kernel, lanes, nrow, ncol, rp, ci, va32, x, y0, True, torch.float32)
+    ref32 = oracle.csr_spmv_f32(nrow, rp, ci, va32, x, y0)
+    if (kernel, lanes) in EXACT:
+        assert_bits(y, ref32, "fp32 in-order")
+    # fp32 oracle per SURVEY.md 8(c): the fp64 reference sum of the fp32-rounded inputs
+    ref64 = oracle.csr_spmv(nrow, ncol, rp, ci, va32.astype(np.float64), x.astype(np.float64), np.zeros(nrow))
+    assert max_row_error(y.astype(np.float64), ref64, row_scale_csr(nrow, rp, ci, va32.astype(np.float64), x.astype(np.float64))) <= TOL32
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_ell_coo_csc_dia_golden(thsp, cuda, name):
+    from arm_spmv_b200 import host as H
+    g = load_golden(name)
+    nrow, ncol = int(g["nrow"]), int(g["ncol"])
+    x, y0 = g["x"], g["y0"]
+    X = H.Vector(x)
+    scale = row_scale_coo(nrow, g["ri"], g["ci"], g["va"], x)
+    # ELL: reference order kept -> bit-identical
+    E = H.ELLMatrix(nrow=nrow, ncol=ncol, nnz=len(g["va"]), nonzeros_in_row=int(g["ell_width"]), col_ind=g["ell_col_ind"],
+                    values=g["ell_values"])
+    Y = H.Vector(y0); H.ELLMatrixMatVector(E, X, Y)
+    assert_bits(host(Y.values), g["y_ell"], f"ell {name}")
+    # COO / CSC: atomics -> tolerance
+    A = H.COOMatrix(nrow, ncol, g["ri"], g["ci"], g["va"])
+    Y = H.Vector(y0); H.COOMatirxMatVector(A, X, Y)
+    assert max_row_error(host(Y.values), g["y_coo"], scale, y0) <= TOL64
+    Cm = H.CSCMatrix(nrow=nrow, ncol=ncol, col_ptr=g["csc_col_ptr"], row_ind=g["csc_row_ind"], values=g["csc_values"])
+    Y = H.Vector(y0); H.CSCMatrixMatVector(Cm, X, Y)
+    assert max_row_error(host(Y.values), g["y_csc"], scale, y0) <= TOL64
+    if "y_dia" in g:
+        D = H.DIAMatrix(nrow=nrow, ncol=ncol, offsets=g["dia_offsets"], values=g["dia_values"])
+        Y = H.Vector(y0); H.DIAMatrixMatVector(D, X, Y)
+        assert_bits(host(Y.values), g["y_dia"], f"dia {name}")
+
+
+@pytest.mark.parametrize("which", ["stencil12", "lap5_40", "rmat12", "uniform"])
+def test_formats_synthetic(thsp, cuda, oracle, which):
+    """All five formats built on the GPU from one COO agree with the oracle's SpMV."""
+    from arm_spmv_b200 import host as H
+    nrow, ncol, rp, ci, va = synthetic(oracle, which)
+    ri = np.repeat(np.arange(nrow, dtype=np.int32), np.diff(rp))
+    rs = np.random.RandomState(1); perm = rs.permutation(len(va))      # unsorted COO
+    ri, cj, v = ri[perm], ci[perm], va[perm]
+    x = oracle.gen_vector(ncol, 3); y0 = oracle.gen_vector(nrow, 4)
+    scale = row_scale_coo(nrow, ri, cj, v, x)
+    A = H.COOMatrix(nrow, ncol, ri, cj, v); X = H.Vector(x)
+    ref = oracle.coo_spmv(nrow, ncol, ri, cj, v, x, y0)
+    Y = H.Vector(y0); H.COOMatirxMatVector(A, X, Y)
+    assert max_row_error(host(Y.values), ref, scale, y0) <= TOL64
+    B = H.CSRMatrix(A); Y = H.Vector(y0); H.CSRMatrixMatVector(B, X, Y)
+    rp2, ci2, va2, _ = oracle.coo2csr(nrow, ncol, ri, cj, v)
+    refc = oracle.csr_spmv(nrow, ncol, rp2, ci2, va2, x, y0)
+    assert max_row_error(host(Y.values), refc, scale, y0) <= TOL64
+    Cc = H.CSCMatrix(A); Y = H.Vector(y0); H.CSCMatrixMatVector(Cc, X, Y)
+    assert max_row_error(host(Y.values), ref, scale, y0) <= TOL64
+    if which != "rmat12":   # ELL width of a power-law matrix is its longest row: keep the slab small
+        D = H.ELLMatrix(A); Y = H.Vector(y0); H.ELLMatrixMatVector(D, X, Y)
+        k, eco, eva, _ = oracle.coo2ell(nrow, ncol, ri, cj, v)
+        assert_bits(host(Y.values), oracle.ell_spmv(nrow, ncol, k, eco, eva, x, y0), f"ell {which}")
+    if which in ("stencil12", "lap5_40"):
+        E = H.DIAMatrix(B); Y = H.Vector(y0); H.DIAMatrixMatVector(E, X, Y)
+        off, dv = oracle.csr2dia(nrow, ncol, rp2, ci2, va2)
+        assert_bits(host(Y.values), oracle.dia_spmv(nrow, ncol, off, dv, x, y0), f"dia {which}")
+
+
+def test_coo_sorted_uses_carry(thsp, cuda, oracle):
+    """Row-sorted COO: same answer as CSR within tolerance (segments chained across steps)."""
+    from arm_spmv_b200 import host as H
+    rp, ci, va = oracle.gen_stencil27_csr(10)
+    nrow = 1000
+    ri = np.repeat(np.arange(nrow, dtype=np.int32), np.diff(rp))
+    x = oracle.gen_vector(nrow, 9)
+    Y = H.Vector(np.zeros(nrow)); H.COOMatirxMatVector(H.COOMatrix(nrow, nrow, ri, ci, va), H.Vector(x), Y)
+    ref = oracle.csr_spmv(nrow, nrow, rp, ci, va, x, np.zeros(nrow))
+    assert max_row_error(host(Y.values), ref, row_scale_csr(nrow, rp, ci, va, x)) <= TOL64

@@ -1,0 +1,142 @@
+"""Pins the CPU oracle (oracle/oracle.c) against the reference's own outputs:
+the committed golden fixtures (generated from the unmodified reference by
+tests/golden/make_golden.py) and, when oracle/_ref/libref.so is present, the live reference.
+Integer/index outputs and every in-order floating-point result must be bit-identical."""
+import numpy as np
+import pytest
+
+import cases as C
+from conftest import load_golden
+
+NAMES = list(C.cases().keys())
+
+
+def eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    assert a.tobytes() == b.tobytes()
+
+
+def test_known_answer_vector(oracle):
+    """SURVEY.md appendix A.1, hand-checked."""
+    I = [3, 1, 0, 1, 3, 1, 0, 3]; J = [4, 2, 0, 0, 3, 2, 3, 0]; V = [1, 2, 3, 4, 5, 6, 7, 8.0]
+    rp, co, va, dg = oracle.coo2csr(4, 5, I, J, V)
+    assert rp.tolist() == [0, 2, 5, 5, 8] and co.tolist() == [0, 3, 2, 0, 2, 4, 3, 0]
+    assert va.tolist() == [3, 7, 2, 4, 6, 1, 5, 8] and dg.tolist() == [3, 5]
+    cp, ro, vc = oracle.coo2csc(4, 5, I, J, V)
+    assert cp.tolist() == [0, 3, 3, 5, 7, 8] and ro.tolist() == [0, 1, 3, 1, 1, 3, 0, 3] and vc.tolist() == [3, 4, 8, 2, 6, 5, 7, 1]
+    k, ec, ev, _ = oracle.coo2ell(4, 5, I, J, V)
+    assert k == 3 and ec.tolist() == [0, 2, 0, 4, 3, 0, 0, 3, 0, 2, 0, 0] and ev.tolist() == [3, 2, 0, 1, 7, 4, 0, 5, 0, 6, 0, 8]
+    off, dv = oracle.csr2dia(4, 5, rp, co, va)
+    assert off.tolist() == [-3, -1, 0, 1, 3]
+    assert dv.tolist() == [0, 0, 3, 0, 7, 0, 4, 0, 6, 0, 0, 0, 0, 0, 0, 8, 0, 5, 1, 0]
+    x = np.arange(1, 6.0); z = np.zeros(4)
+    assert oracle.coo_spmv(4, 5, I, J, V, x, z).tolist() == [31, 28, 0, 33]
+    assert oracle.csr_spmv(4, 5, rp, co, va, x, z + 10).tolist() == [41, 38, 10, 43]   # proves y +=
+    assert oracle.csc_spmv(4, 5, cp, ro, vc, x, z).tolist() == [31, 28, 0, 33]
+    assert oracle.ell_spmv(4, 5, k, ec, ev, x, z).tolist() == [31, 28, 0, 33]
+    assert oracle.dia_spmv(4, 5, off, dv, x, z).tolist() == [31, 22, 0, 28]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_matches_golden(oracle, name):
+    g = load_golden(name)
+    nrow, ncol = int(g["nrow"]), int(g["ncol"])
+    ri, ci, va, x, y0 = g["ri"], g["ci"], g["va"], g["x"], g["y0"]
+    rp, co, cv, dg = oracle.coo2csr(nrow, ncol, ri, ci, va)
+    eq(rp, g["csr_row_ptr"]); eq(co, g["csr_col_ind"]); eq(cv, g["csr_values"]); eq(dg, g["csr_diagonal"])
+    cp, ro, cv2 = oracle.coo2csc(nrow, ncol, ri, ci, va)
+    eq(cp, g["csc_col_ptr"]); eq(ro, g["csc_row_ind"]); eq(cv2, g["csc_values"])
+    k, eco, eva, edg = oracle.coo2ell(nrow, ncol, ri, ci, va)
+    assert k == int(g["ell_width"])
+    eq(eco, g["ell_col_ind"]); eq(eva, g["ell_values"]); eq(edg, g["ell_diagonal"])
+    eq(oracle.coo_spmv(nrow, ncol, ri, ci, va, x, y0), g["y_coo"])
+    eq(oracle.csr_spmv(nrow, ncol, rp, co, cv, x, y0), g["y_csr"])
+    eq(oracle.csc_spmv(nrow, ncol, cp, ro, cv2, x, y0), g["y_csc"])
+    eq(oracle.ell_spmv(nrow, ncol, k, eco, eva, x, y0), g["y_ell"])
+    if "dia_offsets" in g:
+        off, dv = oracle.csr2dia(nrow, ncol, rp, co, cv)
+        eq(off, g["dia_offsets"]); eq(dv, g["dia_values"])
+        if "y_dia" in g:
+            eq(oracle.dia_spmv(nrow, ncol, off, dv, x, y0), g["y_dia"])
+
+
+def test_oracle_vector_ops_match_golden(oracle):
+    g = load_golden("vec_ops")
+    x, y, v = g["x"], g["y"], g["v"]
+    assert oracle.dot(x, y) == float(g["dot"][0])   # one thread: same serial order
+    for i, (a, b) in enumerate(C.AXPBY_COEFFS):
+        eq(oracle.axpby(a, x, b, y), g[f"axpby_{i}"])
+    eq(oracle.fill(17, 3.25), g["fill"])
+    eq(oracle.scale(1.7, v), g["scale"])
+    eq(oracle.shift(-0.3, v), g["shift"])
+    for i, a in enumerate(C.ADD_SCALED_COEFFS):
+        eq(oracle.add_scaled(a, x, v), g[f"add_scaled_{i}"])
+    for i, (a, b) in enumerate(C.ADD2_COEFFS):
+        eq(oracle.add2_scaled(a, x, b, y, v), g[f"add2_scaled_{i}"])
+    assert oracle.check_vector(x, x + 5e-7) and not oracle.check_vector(x, x + 2e-6)
+    assert not oracle.check_vector(x, x[:-1])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_live_reference(oracle, ref, seed):
+    """Random shapes straight against the compiled reference (build container only)."""
+    rs = np.random.RandomState(1000 + seed)
+    nrow, ncol = int(rs.randint(1, 200)), int(rs.randint(1, 200))
+    nnz = int(rs.randint(0, 3000))
+    ri = rs.randint(0, nrow, nnz).astype(np.int32); ci = rs.randint(0, ncol, nnz).astype(np.int32)
+    keep = ~((ri == 0) & (ci == ncol - 1))
+    ri, ci = ri[keep], ci[keep]
+    # the reference's diagonal[] holds nrow entries: drop surplus row==col duplicates
+    d = np.flatnonzero(ri == ci)
+    if len(d) > nrow:
+        drop = np.zeros(len(ri), bool); drop[d[nrow:]] = True
+        ri, ci = ri[~drop], ci[~drop]
+    va = rs.uniform(-1, 1, len(ri)); x = rs.uniform(0, 1, ncol); y0 = rs.uniform(-1, 1, nrow)
+    a = oracle.coo2csr(nrow, ncol, ri, ci, va); b = ref.coo2csr(nrow, ncol, ri, ci, va)
+    for u, w in zip(a, b): eq(u, w)
+    rp, co, cv, _ = a
+    for u, w in zip(oracle.coo2csc(nrow, ncol, ri, ci, va), ref.coo2csc(nrow, ncol, ri, ci, va)): eq(u, w)
+    ea = oracle.coo2ell(nrow, ncol, ri, ci, va); eb = ref.coo2ell(nrow, ncol, ri, ci, va)
+    assert ea[0] == eb[0]
+    for u, w in zip(ea[1:], eb[1:]): eq(u, w)
+    eq(oracle.csr_spmv(nrow, ncol, rp, co, cv, x, y0), ref.csr_spmv(nrow, ncol, rp, co, cv, x, y0))
+    eq(oracle.coo_spmv(nrow, ncol, ri, ci, va, x, y0), ref.coo_spmv(nrow, ncol, ri, ci, va, x, y0))
+    eq(oracle.ell_spmv(nrow, ncol, ea[0], ea[1], ea[2], x, y0), ref.ell_spmv(nrow, ncol, ea[0], ea[1], ea[2], x, y0))
+    da = oracle.csr2dia(nrow, ncol, rp, co, cv); db = ref.csr2dia(nrow, ncol, rp, co, cv)
+    for u, w in zip(da, db): eq(u, w)
+
+
+def test_generators_are_consistent(oracle):
+    """The synthetic matrices the benches use: structure checks on the CPU twins."""
+    rp, ci, va = oracle.gen_stencil27_csr(5)
+    assert rp[-1] == (3 * 5 - 2) ** 3 == len(ci)
+    assert np.all(np.diff(rp) >= 8) and np.all(np.diff(rp) <= 27)
+    for r in (0, 17, 62, 124):
+        cols = ci[rp[r]:rp[r + 1]]
+        assert np.all(np.diff(cols) > 0) and r in cols
+        assert va[rp[r]:rp[r + 1]][list(cols).index(r)] == 26.0
+    sub_rp, sub_ci, sub_va = oracle.gen_stencil27_csr(5, 30, 77)
+    assert np.array_equal(sub_rp, rp[30:78] - rp[30]) and np.array_equal(sub_ci, ci[rp[30]:rp[77]])
+    ri, cj, v = oracle.gen_lap5_coo(6)
+    assert len(v) == 5 * 36 - 4 * 6 and np.all(np.diff(ri) >= 0)
+    ri, cj, v = oracle.gen_uniform_coo(1000, 900, 5000, 43)
+    assert ri.min() >= 0 and ri.max() < 1000 and cj.max() < 900 and 0 <= v.min() and v.max() < 1
+    ri, cj, v = oracle.gen_rmat_coo(10, 8000, 42)
+    assert ri.max() < 1024 and cj.max() < 1024
+    assert np.bincount(ri, minlength=1024).max() > 20 * 8000 / 1024   # power-law head
+
+
+def test_partition_and_slice(oracle):
+    """src/mat_vec.cpp:233-263: equal row blocks, remainder to the last, row_ptr rebased to 0."""
+    rp, ci, va = oracle.gen_stencil27_csr(4)
+    n = 64
+    for parts in (1, 2, 3, 8):
+        covered = 0
+        for p in range(parts):
+            s, c = oracle.partition(n, parts, p)
+            assert s == covered
+            covered += c
+            sub, nnz = oracle.csr_slice(rp, s, c)
+            assert sub[0] == 0 and sub[-1] == nnz == rp[s + c] - rp[s]
+        assert covered == n
