@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(256) hist_kernel(int n, const int* __restrict_
     for (int it = 0; it < rounds; ++it) {
         const int k = it * stride + blockIdx.x * 256 + threadIdx.x;
         const int mine = k < n ? ld_stream(key + k) : -1;
-        int prev = __shfl_up_sync(full, mine, 1);
-        if (lane == 0) prev = (k > 0 && k < n) ? ld_stream(key + k - 1) : -1;
+        const int up = __shfl_up_sync(full, mine, 1);  // every lane takes part: never inside a short-circuit
+        const int prev = lane == 0 ? ((k > 0 && k < n) ? ld_stream(key + k - 1) : -1) : up;
         if (k < n && k > 0 && prev > mine) bad = 1;
-        const bool head = (lane == 0) || (__shfl_up_sync(full, mine, 1) != mine);
+        const bool head = (lane == 0) || (up != mine);
         const unsigned heads = __ballot_sync(full, head);
         if (head && mine >= 0) {
             const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1)) << (lane + 1);
