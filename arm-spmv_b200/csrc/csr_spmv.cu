@@ -109,11 +109,12 @@ __host__ __device__ inline size_t stream_warp_bytes(int stages, int chunk)
 }
 
 template <typename V>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;
@@ -137,105 +138,120 @@ __global__ void __launch_bounds__(512, 1)
     const int nnz_al = nnz & ~3;
     const uint64_t pol = policy_evict_first();
 
-    // ---- producer cursor (warp-uniform) -------------------------------------------------
+    // ---- producer cursor (warp-uniform): runs S chunks ahead of the consumer --------------
     int p_tile = gw, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
     bool p_open = false;
     int pf_rs = 0, pf_re = 0;  // row bounds of p_tile, fetched one step ahead
     if (p_tile < num_tiles) {
-        int r = p_tile * 32 + lane;
+        const int r = p_tile * 32 + lane;
         pf_rs = __ldg(row_ptr + min(r, nrow));
         pf_re = __ldg(row_ptr + min(r + 1, nrow));
     }
-
-    auto produce = [&]() {
-        if (p_tile >= num_tiles) return;
-        if (!p_open) {
-            s_rs[p_slot * 32 + lane] = pf_rs;
-            s_re[p_slot * 32 + lane] = pf_re;
-            const int ts = __shfl_sync(0xffffffffu, pf_rs, 0);
-            p_te = __shfl_sync(0xffffffffu, pf_re, 31);
-            p_al = ts & ~3;
-            p_nch = max(1, (p_te - p_al + CH - 1) / CH);
-            p_chunk = 0;
-            p_open = true;
-            const int nt = p_tile + GW;  // bounds of the tile after this one
-            if (nt < num_tiles) {
-                int r = nt * 32 + lane;
-                pf_rs = __ldg(row_ptr + min(r, nrow));
-                pf_re = __ldg(row_ptr + min(r + 1, nrow));
-            }
-        }
-        const int g0 = p_al + p_chunk * CH;
-        const int g1 = min(g0 + CH, p_te);
-        const int t1 = min((g1 + 3) & ~3, nnz_al);
-        const int nt = max(t1 - g0, 0);
-        V* dv = s_val + (size_t)p_stage * stage_elems;
-        int* dc = s_col + (size_t)p_stage * stage_elems;
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar + p_stage, (unsigned)nt * (unsigned)(sizeof(V) + sizeof(int)));
-            if (nt > 0) {
-                bulk_g2s(dv, val + g0, (unsigned)nt * (unsigned)sizeof(V), bar + p_stage, pol);
-                bulk_g2s(dc, col + g0, (unsigned)nt * (unsigned)sizeof(int), bar + p_stage, pol);
-            }
-        }
-        if (g1 > nnz_al) {  // ragged end of the arrays: at most 3 entries
-            const int g = max(g0, nnz_al) + lane;
-            if (g < g1) {
-                dv[g - g0] = val[g];
-                dc[g - g0] = col[g];
-            }
-        }
-        p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
-        if (++p_chunk == p_nch) {
-            p_tile += GW;
-            p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
-            p_open = false;
-        }
-    };
-
-    for (int i = 0; i < S - 1; ++i) produce();
-
-    // ---- consumer ---------------------------------------------------------------------
-    int c_slot = 0, c_stage = 0;
+    // ---- consumer cursor ------------------------------------------------------------------
+    int c_tile = gw, c_slot = 0, c_chunk = 0, c_nch = 1, c_al = 0, c_te = 0, c_stage = 0;
     unsigned c_parity = 0;
-    for (int tile = gw; tile < num_tiles; tile += GW) {
-        produce();  // may open this very tile when S == 1
-        const int row = tile * 32 + lane;
-        const int rs = s_rs[c_slot * 32 + lane];
-        const int re = s_re[c_slot * 32 + lane];
-        c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
-        const int ts = __shfl_sync(0xffffffffu, rs, 0);
-        const int te = __shfl_sync(0xffffffffu, re, 31);
-        const int al = ts & ~3;
-        const int nch = max(1, (te - al + CH - 1) / CH);
-        V yold = V(0);
-        if (accumulate && row < nrow) yold = y[row];
-        V sum = V(0);
-        for (int c = 0; c < nch; ++c) {
-            if (c > 0) produce();
-            mbar_wait(bar + c_stage, c_parity);
-            __syncwarp();
-            const int g0 = al + c * CH;
-            const int g1 = min(g0 + CH, te);
+    int rs = 0, re = 0;
+    V sum = V(0), yold = V(0);
+    int lead = S - 1;  // produce-only iterations that fill the ring
+
+    // One loop, one produce site, one consume site (keeps the code - and the registers - small).
+    while (true) {
+        // ================= produce one chunk =================
+        if (p_tile < num_tiles) {
+            if (!p_open) {
+                s_rs[p_slot * 32 + lane] = pf_rs;
+                s_re[p_slot * 32 + lane] = pf_re;
+                const int ts = __shfl_sync(full, pf_rs, 0);
+                p_te = __shfl_sync(full, pf_re, 31);
+                p_al = ts & ~3;
+                p_nch = max(1, (p_te - p_al + CH - 1) / CH);
+                p_chunk = 0;
+                p_open = true;
+                const int nt = p_tile + GW;  // bounds of the tile after this one
+                if (nt < num_tiles) {
+                    const int r = nt * 32 + lane;
+                    pf_rs = __ldg(row_ptr + min(r, nrow));
+                    pf_re = __ldg(row_ptr + min(r + 1, nrow));
+                }
+            }
+            const int g0 = p_al + p_chunk * CH;
+            const int g1 = min(g0 + CH, p_te);
+            const int t1 = min((g1 + 3) & ~3, nnz_al);
+            const int nt = max(t1 - g0, 0);
+            V* dv = s_val + (size_t)p_stage * stage_elems;
+            int* dc = s_col + (size_t)p_stage * stage_elems;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar + p_stage, (unsigned)nt * (unsigned)(sizeof(V) + sizeof(int)));
+                if (nt > 0) {
+                    bulk_g2s(dv, val + g0, (unsigned)nt * (unsigned)sizeof(V), bar + p_stage, pol);
+                    bulk_g2s(dc, col + g0, (unsigned)nt * (unsigned)sizeof(int), bar + p_stage, pol);
+                }
+            }
+            if (g1 > nnz_al) {  // ragged end of the arrays: at most 3 entries
+                const int g = max(g0, nnz_al) + lane;
+                if (g < g1) {
+                    dv[g - g0] = val[g];
+                    dc[g - g0] = col[g];
+                }
+            }
+            p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
+            if (++p_chunk == p_nch) {
+                p_tile += GW;
+                p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
+                p_open = false;
+            }
+        }
+        if (lead > 0) {
+            --lead;
+            continue;
+        }
+        // ================= consume one chunk =================
+        if (c_tile >= num_tiles) break;
+        const int row = c_tile * 32 + lane;
+        if (c_chunk == 0) {
+            rs = s_rs[c_slot * 32 + lane];
+            re = s_re[c_slot * 32 + lane];
+            const int ts = __shfl_sync(full, rs, 0);
+            c_te = __shfl_sync(full, re, 31);
+            c_al = ts & ~3;
+            c_nch = max(1, (c_te - c_al + CH - 1) / CH);
+            sum = V(0);
+            yold = (accumulate && row < nrow) ? y[row] : V(0);
+        }
+        mbar_wait(bar + c_stage, c_parity);
+        __syncwarp();
+        {
+            const int g0 = c_al + c_chunk * CH;
+            const int g1 = min(g0 + CH, c_te);
             const V* sv = s_val + (size_t)c_stage * stage_elems - g0;
             const int* sc = s_col + (size_t)c_stage * stage_elems - g0;
             const int lo = max(rs, g0), hi = min(re, g1);
-            int j = lo;
-            for (; j + 3 < hi; j += 4) {
-                const int c0 = sc[j], c1 = sc[j + 1], c2 = sc[j + 2], c3 = sc[j + 3];
-                const V x0 = ld_gather(x + c0), x1 = ld_gather(x + c1), x2 = ld_gather(x + c2), x3 = ld_gather(x + c3);
-                sum = add_rn(sum, mul_rn(sv[j], x0));
-                sum = add_rn(sum, mul_rn(sv[j + 1], x1));
-                sum = add_rn(sum, mul_rn(sv[j + 2], x2));
-                sum = add_rn(sum, mul_rn(sv[j + 3], x3));
+            // U entries in flight per lane: all index loads, all x gathers, then the in-order adds.
+            constexpr int U = 9;
+            for (int j = lo; j < hi; j += U) {
+                int cc[U];
+                V xx[U], vv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) cc[u] = (j + u < hi) ? sc[j + u] : 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) xx[u] = (j + u < hi) ? ld_gather(x + cc[u]) : V(0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) vv[u] = (j + u < hi) ? sv[j + u] : V(0);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (j + u < hi) sum = add_rn(sum, mul_rn(vv[u], xx[u]));  // skipped, not "+0": keeps -0.0 sums exact
             }
-            for (; j < hi; ++j) sum = add_rn(sum, mul_rn(sv[j], ld_gather(x + sc[j])));
-            __syncwarp();
-            c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
-            if (c_stage == 0) c_parity ^= 1u;
         }
-        if (row < nrow) y[row] = accumulate ? add_rn(yold, sum) : sum;
+        __syncwarp();
+        c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
+        if (c_stage == 0) c_parity ^= 1u;
+        if (++c_chunk == c_nch) {
+            if (row < nrow) y[row] = accumulate ? add_rn(yold, sum) : sum;
+            c_tile += GW;
+            c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
+            c_chunk = 0;
+        }
     }
 }
 
@@ -245,7 +261,7 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
-    THSP_REQUIRE(cfg.chunk % 4 == 0 && cfg.chunk >= 32 && cfg.stages >= 1 && cfg.warps >= 1 && cfg.warps <= 16,
+    THSP_REQUIRE(cfg.chunk % 4 == 0 && cfg.chunk >= 32 && cfg.stages >= 1 && cfg.warps >= 1 && cfg.warps <= 24,
                  "bad stream configuration");
     size_t smem = stream_warp_bytes<V>(cfg.stages, cfg.chunk) * (size_t)cfg.warps;
     THSP_REQUIRE(smem <= 227 * 1024, "stream configuration exceeds 227 KB of shared memory");
@@ -263,23 +279,24 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     return 0;
 }
 
-// Stage size from the mean row length: one 32-row tile should fit one stage.
+// Default shape: one 32-row tile fits one stage, and as many warps as shared memory and the
+// 768-thread launch bound allow.  Measured on B200 (profiles/): the kernel is bound by the
+// latency of a tile's load -> gather -> sum chain, so warps in flight matter more than ring
+// depth; S = 1 with 16+ warps beats S = 2 with 8.
 template <typename V>
 static StreamCfg default_stream_cfg(int nrow, int nnz)
 {
     double mean = nrow > 0 ? (double)nnz / nrow : 0.0;
-    int want = (int)(mean * 32.0 * 1.05) + 16;
+    int want = (int)(mean * 32.0 * 1.02) + 8;
     int chunk = 128;
-    while (chunk < want && chunk < 2048) chunk += 128;
+    while (chunk < want && chunk < 2048) chunk += 32;
     StreamCfg c;
     c.chunk = chunk;
-    c.warps = 8;
-    c.stages = 2;
-    // use what shared memory allows: prefer deeper rings, then more warps
-    auto fits = [&](int w, int s) { return stream_warp_bytes<V>(s, chunk) * (size_t)w <= 200 * 1024; };
-    while (c.stages < 4 && fits(c.warps, c.stages + 1)) ++c.stages;
-    while (c.warps < 16 && fits(c.warps + 1, c.stages)) ++c.warps;
-    while (c.warps > 1 && !fits(c.warps, c.stages)) --c.warps;
+    c.stages = 1;
+    c.warps = 1;
+    auto fits = [&](int w, int s) { return stream_warp_bytes<V>(s, chunk) * (size_t)w <= 220 * 1024; };
+    while (c.warps < 24 && fits(c.warps + 1, c.stages)) ++c.warps;
+    while (c.stages < 4 && c.warps >= 16 && fits(c.warps, c.stages + 1)) ++c.stages;
     return c;
 }
 
