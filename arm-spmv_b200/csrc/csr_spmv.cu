@@ -265,8 +265,10 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
                  "bad stream configuration");
     size_t smem = stream_warp_bytes<V>(cfg.stages, cfg.chunk) * (size_t)cfg.warps;
     THSP_REQUIRE(smem <= 227 * 1024, "stream configuration exceeds 227 KB of shared memory");
-    static size_t configured[2] = {0, 0};
-    size_t& cur = configured[sizeof(V) == 8 ? 0 : 1];
+    static size_t configured[16][2] = {};  // the attribute is per device
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    size_t& cur = configured[dev & 15][sizeof(V) == 8 ? 0 : 1];
     if (smem > cur) {
         THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cur = 227 * 1024;

@@ -201,13 +201,15 @@ __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, const int*
 // order, including its `j < nrow` guard (:140).
 static constexpr int kDiaRows = 128;
 
-__global__ void __launch_bounds__(kDiaRows) dia_kernel(int nrow, int ndiags, const int* __restrict__ off,
-                                                       const double* __restrict__ values, const double* __restrict__ x,
-                                                       double* __restrict__ y, int staged)
+__global__ void __launch_bounds__(kDiaRows) dia_kernel(int row_begin, int nrows, int nrow_total, int ndiags,
+                                                       const int* __restrict__ off, const double* __restrict__ values,
+                                                       const double* __restrict__ x, double* __restrict__ y, int staged)
 {
+    // values / y point at the block's first row; x is the whole vector; the column guard uses
+    // the GLOBAL row index against the global row count (the non-partitioned semantics).
     extern __shared__ double s_v[];
     const int r0 = blockIdx.x * kDiaRows;
-    const int nr = min(kDiaRows, nrow - r0);
+    const int nr = min(kDiaRows, nrows - r0);
     const int i = r0 + threadIdx.x;
     if (staged) {
         const size_t base = (size_t)r0 * ndiags;
@@ -215,11 +217,11 @@ __global__ void __launch_bounds__(kDiaRows) dia_kernel(int nrow, int ndiags, con
         for (int t = threadIdx.x; t < total; t += kDiaRows) s_v[t + t / 32] = ld_stream(values + base + t);
         __syncthreads();
     }
-    if (i >= nrow) return;
+    if (i >= nrows) return;
     double acc = y[i];
     for (int d = 0; d < ndiags; ++d) {
-        const int j = i + __ldg(off + d);
-        if (j >= 0 && j < nrow) {
+        const int j = row_begin + i + __ldg(off + d);
+        if (j >= 0 && j < nrow_total) {
             const int t = threadIdx.x * ndiags + d;
             const double v = staged ? s_v[t + t / 32] : __ldg(values + (size_t)i * ndiags + d);
             acc = add_rn(acc, mul_rn(v, ld_gather(x + j)));
@@ -280,19 +282,25 @@ int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int
     return 0;
 }
 
+int thsp_dia_spmv_rows_f64(int row_begin, int row_count, int nrow, int ndiags, const int* offsets, const double* values,
+                           const double* x, double* y, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (row_count <= 0 || ndiags <= 0) return 0;
+    const size_t words = (size_t)kDiaRows * ndiags;
+    const size_t smem = (words + words / 32 + 1) * sizeof(double);
+    const int staged = smem <= 48 * 1024 ? 1 : 0;
+    dia_kernel<<<div_up(row_count, kDiaRows), kDiaRows, staged ? smem : 0, as_stream(stream)>>>(row_begin, row_count, nrow, ndiags,
+                                                                                               offsets, values, x, y, staged);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
 int thsp_dia_spmv_f64(int nrow, int ncol, int ndiags, const int* offsets, const double* values, const double* x,
                       double* y, thsp_stream_t stream)
 {
     (void)ncol;
-    if (ensure_device()) return 1;
-    if (nrow <= 0 || ndiags <= 0) return 0;
-    const size_t words = (size_t)kDiaRows * ndiags;
-    const size_t smem = (words + words / 32 + 1) * sizeof(double);
-    const int staged = smem <= 48 * 1024 ? 1 : 0;
-    dia_kernel<<<div_up(nrow, kDiaRows), kDiaRows, staged ? smem : 0, as_stream(stream)>>>(nrow, ndiags, offsets, values,
-                                                                                          x, y, staged);
-    THSP_LAUNCH_CHECK();
-    return 0;
+    return thsp_dia_spmv_rows_f64(0, nrow, nrow, ndiags, offsets, values, x, y, stream);
 }
 
 }  // extern "C"

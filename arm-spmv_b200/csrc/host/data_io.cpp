@@ -1,0 +1,120 @@
+// data_io.cpp -- file readers/writers of the arm-spmv API (replaces src/data_io.cpp).
+//
+// Text parsing is CPU work and stays on the CPU.  What differs
+// from the reference: the parsed arrays are written into CUDA managed memory so the next GPU
+// call can use them without a staging copy, and CSR/CSC/ELL readers convert with the GPU
+// constructors (the reference's operator=(COO) leaves row_ptr[nrow] uninitialised, A.3).
+#include "data_io.h"
+
+#include <stdlib.h>
+
+#include "hostmem.h"
+#include "mmio.h"
+
+using namespace thsp_host;
+
+void VectorRead(const char* filename, Vector& x)
+{
+    FILE* fp = fopen(filename, "r");
+    if (!fp) {
+        printf("***Failed to open vector file %s ***\n", filename);
+        exit(1);
+    }
+    int n = 0;
+    if (fscanf(fp, "%d", &n) != 1 || n < 0) n = 0;
+    double* v = alloc<double>(n);
+    for (int i = 0; i < n; ++i)
+        if (fscanf(fp, "\n%lg", &v[i]) != 1) v[i] = 0.0;
+    fclose(fp);
+    x.Free();
+    x.size = n;
+    x.values = v;
+}
+
+void VectorWrite(const char* filename, const Vector& x)
+{
+    FILE* fp = fopen(filename, "w");
+    if (!fp) {
+        printf("***Failed to open vector file %s ***\n", filename);
+        exit(1);
+    }
+    fprintf(fp, "%d", x.size);
+    if (x.size > 0) {
+        // one host-side pass; managed pages migrate back on demand
+        sync();
+        for (int i = 0; i < x.size; ++i) fprintf(fp, "\n%20.16g", x.values[i]);
+    }
+    fclose(fp);
+}
+
+void COOMatrixRead(const char* filename, COOMatrix& A)
+{
+    // Progress lines and failure behaviour follow src/data_io.cpp:52-91 (print, exit(1)).
+    printf("\tOpening matrix market file\n");
+    FILE* fp = fopen(filename, "r");
+    if (!fp) {
+        printf("***Failed to open MatrixMarket file %s ***\n", filename);
+        exit(1);
+    }
+    printf("\tReading MatrixMarket banner\n");
+    MM_typecode code;
+    if (mm_read_banner(fp, &code) != 0) {
+        printf("*** Could not process Matrix Market banner ***\n");
+        exit(1);
+    }
+    if (mm_is_complex(code) && mm_is_matrix(code) && mm_is_sparse(code)) {
+        char* s = mm_typecode_to_str(code);
+        printf("Sorry, this application does not support Market Market type: [%s]\n", s ? s : "?");
+        free(s);
+        exit(1);
+    }
+    printf("\tReading sparse matrix size...");
+    int rows = 0, cols = 0, nz = 0;
+    if (mm_read_mtx_crd_size(fp, &rows, &cols, &nz) != 0) exit(1);
+    printf("\tAllocating memory for matrix\n");
+    int* ri = alloc<int>(nz);
+    int* ci = alloc<int>(nz);
+    double* va = alloc<double>(nz);
+    printf("\tReading matrix entries from file\n");
+    for (int k = 0; k < nz; ++k) {
+        int i = 0, j = 0;
+        double v = 0.0;
+        if (fscanf(fp, "%d %d %lg\n", &i, &j, &v) != 3) {
+            printf("*** Matrix Market file ended after %d of %d entries ***\n", k, nz);
+            exit(1);
+        }
+        ri[k] = i - 1;  // file is 1-based
+        ci[k] = j - 1;
+        va[k] = v;
+    }
+    if (fp != stdin) fclose(fp);
+    printf("### ROW=%d, COL=%d, NNZ=%d\n", rows, cols, nz);
+    A.Free();
+    A.nrow = rows;
+    A.ncol = cols;
+    A.nnz = nz;
+    A.row_ind = ri;
+    A.col_ind = ci;
+    A.values = va;
+}
+
+void CSRMatrixRead(const char* filename, CSRMatrix& A)
+{
+    COOMatrix B;
+    COOMatrixRead(filename, B);
+    A = B;
+}
+
+void CSCMatrixRead(const char* filename, CSCMatrix& A)
+{
+    COOMatrix B;
+    COOMatrixRead(filename, B);
+    A = B;
+}
+
+void ELLMatrixRead(const char* filename, ELLMatrix& A)
+{
+    COOMatrix B;
+    COOMatrixRead(filename, B);
+    A = B;
+}

@@ -131,6 +131,11 @@ THSP_API int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, 
 /* DIAMatrixMatVector (src/mat_vec.cpp:123-146): row-major values[i*ndiags+d], guard j<nrow. */
 THSP_API int thsp_dia_spmv_f64(int nrow, int ncol, int ndiags, const int* offsets, const double* values,
                                const double* x, double* y, thsp_stream_t stream);
+/* Row block [row_begin, row_begin+row_count) of the same product: `values` and `y` point at the
+ * block's first row, x is the whole vector, nrow the whole matrix' row count (the column guard).
+ * DIAMatrixMatVectorNumaThread (src/mat_vec.cpp:580-606) with a global, not block-local, guard. */
+THSP_API int thsp_dia_spmv_rows_f64(int row_begin, int row_count, int nrow, int ndiags, const int* offsets,
+                                    const double* values, const double* x, double* y, thsp_stream_t stream);
 
 /* -------------------------------------------------------------- conversions -------- */
 /* All are stable: within a row (column) entries keep their COO order and duplicates are kept,
