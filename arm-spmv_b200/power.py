@@ -1,0 +1,433 @@
+"""Row-partitioned repeated SpMV (power iteration) across the GPUs of one box.
+
+This is what the reference's NUMA placement (src/mat_vec.cpp:230-297, include/numa_node.h)
+becomes on B200s: one process per GPU (torchrun), each owning an equal block of rows
+(`rows_per_node = nrow / nparts`, last block takes the remainder, :233,245-246) with row
+pointers rebased to 0 (:260-263), a full-length replica of x (:257,266) and its own slice of y.
+The reference never refreshes x between its 50 repeats; the north star asks for a real iterated
+loop, composed from the reference's own vector ops:
+
+    y = A x                      CSRMatrixMatVector          (thsp_csr_plan_spmv_f64)
+    s = sum y_i^2 ; all-reduce   vec_dot(y, y)               (thsp_sumsq_dev_f64 + NCCL, 8 bytes)
+    x_own = y / sqrt(s)          vec_axpby(1/nrm, y, 0, ...) (thsp_scale_broadcast_f64)
+    refresh the replicas of x    -- no reference counterpart --
+
+x refresh modes
+  allgather  NCCL all-gather of every slice into every replica (the north star's wording).
+  fused      the scale kernel stores each normalised value straight into all replicas through
+             NVLink peer pointers (torch symmetric memory): compute + "all-gather" in one kernel.
+  halo       column-footprint analysis: a block only needs x over [min col, max col] of its rows;
+             only the parts of that range owned by other ranks are pulled.
+With `overlap`, rows whose columns all fall inside the own slice (interior) are multiplied while
+the refresh is still in flight; the boundary blocks wait for it.
+
+Row blocks hold fewer than 2^31 entries each, so int32 row pointers survive matrices (512^3:
+3.6e9 entries) that the reference's structs cannot represent.
+
+The arithmetic lives behind an `ops` object.  The product uses CudaOps (the C ABI).  The CPU
+tests (gloo, world_size 2) inject their own ops built on the oracle - this module has no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+import time
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+
+def partition_rows(n: int, nparts: int, part: int) -> tuple[int, int]:
+    """(start, count) of block `part`: src/mat_vec.cpp:233,245-246."""
+    per = n // nparts
+    start = part * per
+    return start, (n - start) if part == nparts - 1 else per
+
+
+def stencil_row_blocks(n: int, start: int, count: int, world: int, max_rows: int) -> list[tuple[int, int, bool]]:
+    """Split rows [start, start+count) of the n^3 27-point stencil into (r0, r1, boundary) pieces.
+    Boundary pieces are the first / last grid plane of the slab when another rank owns the
+    neighbouring plane; interior pieces are cut so that each holds < 2^31 entries."""
+    end = start + count
+    plane = n * n
+    reach = plane + n + 1            # furthest column offset of a row
+    pieces = []
+    lo, hi = start, end
+    if world > 1 and start > 0:
+        b = min(end, start + reach)
+        pieces.append((start, b, True))
+        lo = b
+    tail = None
+    if world > 1 and end < n ** 3 and hi - reach > lo:
+        tail = (hi - reach, hi, True)
+        hi -= reach
+    elif world > 1 and end < n ** 3 and hi > lo:
+        tail = (lo, hi, True)
+        hi = lo
+    r = lo
+    while r < hi:
+        e = min(hi, r + max_rows)
+        pieces.append((r, e, False))
+        r = e
+    if tail:
+        pieces.append(tail)
+    return pieces
+
+
+@dataclass
+class RowBlock:
+    row0: int            # first global row
+    nrow: int
+    nnz: int
+    boundary: bool       # needs x entries owned by another rank
+    payload: object      # ops-specific (device CSR + plan)
+    col_min: int = 0
+    col_max: int = 0
+
+
+class CudaOps:
+    """The product arithmetic: every call goes through libthsparse_cuda.so on torch's current stream."""
+
+    def __init__(self, device):
+        from . import host as H
+        from .lib import check, current_stream, load, ptr
+        self.H, self.check, self.stream, self.lib, self.ptr = H, check, current_stream, load(), ptr
+        self.device = device
+
+    def empty(self, n):
+        return torch.empty(n, dtype=torch.float64, device=self.device)
+
+    def scalar(self):
+        return torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    def stencil_block(self, n, r0, r1):
+        A = self.H.stencil27_csr(n, r0, r1, device=self.device)
+        A.plan()
+        return A, A.nnz
+
+    def csr_block(self, nrow, ncol, row_ptr, col_ind, values):
+        A = self.H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=row_ptr, col_ind=col_ind, values=values, device=self.device)
+        A.plan()
+        return A, A.nnz
+
+    def spmv(self, payload, x, y):
+        """y = A_block x (overwrite: saves Fill(0) and the read of y)."""
+        self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
+
+    def sumsq(self, y, out):
+        self.check(self.lib.thsp_sumsq_dev_f64(C.c_int64(y.numel()), self.ptr(y), self.ptr(out), self.stream()))
+
+    def scale_into(self, y, sumsq, x, offset, peer_ptrs=None):
+        """x_k[offset + i] = y[i] / sqrt(sumsq): into the local replica `x`, or into every replica
+        in peer_ptrs (device pointers mapped over NVLink) when given."""
+        dst_ptrs = peer_ptrs if peer_ptrs else [x.data_ptr()]
+        arr = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+        self.check(self.lib.thsp_scale_broadcast_f64(C.c_int64(y.numel()), self.ptr(y), self.ptr(sumsq), arr, len(dst_ptrs),
+                                                     C.c_int64(offset), self.stream()))
+
+    def col_range(self, payload):
+        c = payload.col_ind
+        if c.numel() == 0:
+            return 0, -1
+        return int(c.min().item()), int(c.max().item())
+
+
+class PartitionedCSR:
+    """This rank's rows of a square matrix, as a list of RowBlocks (interior first is not required)."""
+
+    def __init__(self, n_global: int, rank: int, world: int, start: int, count: int, blocks: list[RowBlock]):
+        self.N, self.rank, self.world, self.start, self.count, self.blocks = n_global, rank, world, start, count, blocks
+        self.nnz_local = sum(b.nnz for b in blocks)
+
+    @staticmethod
+    def stencil27(n: int, rank: int, world: int, ops, max_block_rows: int = 1 << 26) -> "PartitionedCSR":
+        N = n ** 3
+        start, count = partition_rows(N, world, rank)
+        blocks = []
+        for r0, r1, bnd in stencil_row_blocks(n, start, count, world, max_block_rows):
+            payload, nnz = ops.stencil_block(n, r0, r1)
+            reach = n * n + n + 1
+            blocks.append(RowBlock(r0, r1 - r0, nnz, bnd, payload, max(0, r0 - reach), min(N - 1, r1 - 1 + reach)))
+        return PartitionedCSR(N, rank, world, start, count, blocks)
+
+    @staticmethod
+    def from_csr(nrow: int, row_ptr, col_ind, values, rank: int, world: int, ops) -> "PartitionedCSR":
+        """Generic square CSR given as torch tensors: slice this rank's rows and rebase row_ptr
+        exactly as CSRMatrixMatVectorNuma does (src/mat_vec.cpp:245-265)."""
+        start, count = partition_rows(nrow, world, rank)
+        e0, e1 = int(row_ptr[start]), int(row_ptr[start + count])
+        sub_rp = (row_ptr[start:start + count + 1] - e0).to(torch.int32).contiguous()
+        payload, nnz = ops.csr_block(count, nrow, sub_rp, col_ind[e0:e1].contiguous(), values[e0:e1].contiguous())
+        lo, hi = ops.col_range(payload)
+        bnd = world > 1 and (lo < start or hi >= start + count)
+        return PartitionedCSR(nrow, rank, world, start, count, [RowBlock(start, count, nnz, bnd, payload, lo, hi)])
+
+    def spmv(self, ops, x, y_local, boundary: bool | None = None):
+        for b in self.blocks:
+            if boundary is None or b.boundary == boundary:
+                off = b.row0 - self.start
+                ops.spmv(b.payload, x, y_local[off:off + b.nrow])
+
+    def needed_ranges(self) -> list[tuple[int, int, int]]:
+        """(owner rank, lo, hi) pieces of x outside the own slice that the boundary blocks read."""
+        lo = min((b.col_min for b in self.blocks if b.boundary), default=self.start)
+        hi = max((b.col_max for b in self.blocks if b.boundary), default=self.start + self.count - 1) + 1
+        out = []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            s, c = partition_rows(self.N, self.world, r)
+            a, b = max(lo, s), min(hi, s + c)
+            if a < b:
+                out.append((r, a, b))
+        return out
+
+
+class PowerIteration:
+    def __init__(self, A: PartitionedCSR, ops, exchange: str = "allgather", overlap: bool = True, group=None, seed: int = 11):
+        self.A, self.ops, self.exchange, self.overlap, self.group = A, ops, exchange, overlap, group
+        self.world, self.rank = A.world, A.rank
+        self.y = ops.empty(A.count)
+        self.ss = ops.scalar()
+        self.symm = None
+        if self.world > 1 and exchange in ("fused", "halo"):
+            import torch.distributed._symmetric_memory as symm_mem
+            self.x = symm_mem.empty(A.N, dtype=torch.float64, device=ops.device)
+            self.symm = symm_mem.rendezvous(self.x, group=dist.group.WORLD.group_name if group is None else group.group_name)
+            self.peer_ptrs = [int(self.symm.buffer_ptrs[r]) for r in range(self.world)]
+        else:
+            self.x = ops.empty(A.N)
+            self.peer_ptrs = None
+        self.comm_stream = torch.cuda.Stream(device=ops.device) if (self.world > 1 and ops.device.type == "cuda") else None
+        self.x_ready = None  # event: remote parts of x are fresh
+        self.equal_split = A.N % self.world == 0
+        self._init_x(seed)
+
+    def _init_x(self, seed):
+        # x0 = the same counter-hash vector on every rank (thsp_gen_vector_f64 / oracle_gen_vector)
+        if hasattr(self.ops, "init_x"):
+            self.ops.init_x(self.x, seed)
+        else:
+            H = self.ops.H
+            self.ops.check(self.ops.lib.thsp_gen_vector_f64(C.c_int64(self.A.N), C.c_uint64(seed), self.ops.ptr(self.x), self.ops.stream()))
+        if self.symm is not None:
+            torch.cuda.synchronize()
+            self.symm.barrier()
+
+    # ---- one iteration ------------------------------------------------------------------
+    def step(self):
+        A, ops = self.A, self.ops
+        cur = torch.cuda.current_stream() if self.comm_stream is not None else None
+        if self.world > 1 and self.overlap:
+            A.spmv(ops, self.x, self.y, boundary=False)      # needs only the own slice of x
+            self._wait_refresh(cur)
+            A.spmv(ops, self.x, self.y, boundary=True)
+        else:
+            self._wait_refresh(cur)
+            A.spmv(ops, self.x, self.y)
+        ops.sumsq(self.y, self.ss)
+        if self.world > 1:
+            dist.all_reduce(self.ss, group=self.group)        # 8 bytes
+        self._scale_and_refresh(cur)
+
+    def _wait_refresh(self, cur):
+        if self.x_ready is not None and cur is not None:
+            cur.wait_event(self.x_ready)
+
+    def _scale_and_refresh(self, cur):
+        A, ops = self.A, self.ops
+        if self.world == 1:
+            ops.scale_into(self.y, self.ss, self.x, A.start)
+            return
+        if self.exchange == "fused":
+            # One kernel: normalise and store into every replica over NVLink.  The barrier makes
+            # the stores of all ranks visible before anyone's boundary rows read them.
+            ops.scale_into(self.y, self.ss, self.x, A.start, peer_ptrs=self.peer_ptrs)
+            self._barrier_async(cur)
+            return
+        ops.scale_into(self.y, self.ss, self.x, A.start)
+        if self.exchange == "halo":
+            self._barrier_async(cur, pull=True)
+            return
+        # NCCL all-gather of the slices, in place, on the side stream
+        done = torch.cuda.Event() if cur is not None else None
+        if cur is not None:
+            done.record(cur)
+            self.comm_stream.wait_event(done)
+        ctx = torch.cuda.stream(self.comm_stream) if self.comm_stream is not None else _Null()
+        with ctx:
+            own = self.x[A.start:A.start + A.count]
+            _all_gather_slices(self.x, own, A.N, self.world, self.equal_split, self.group)
+            if self.comm_stream is not None:
+                self.x_ready = torch.cuda.Event()
+                self.x_ready.record(self.comm_stream)
+
+    def _barrier_async(self, cur, pull=False):
+        """Symmetric-memory barrier on the side stream (and, for `halo`, the pulls of the needed
+        pieces of x from their owners' replicas), so interior rows can start meanwhile."""
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.comm_stream.wait_event(done)
+        with torch.cuda.stream(self.comm_stream):
+            self.symm.barrier()
+            if pull:
+                for owner, lo, hi in self.A.needed_ranges():
+                    src = self.symm.get_buffer(owner, (self.A.N,), torch.float64)
+                    self.x[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                # no second barrier: an owner overwrites its slice only after the next all-reduce,
+                # which this rank joins after the rows that read these pieces have been multiplied
+            self.x_ready = torch.cuda.Event()
+            self.x_ready.record(self.comm_stream)
+
+    def norm(self) -> float:
+        """||A x|| of the last step (the power-iteration eigenvalue estimate), on the host."""
+        return math.sqrt(float(self.ss.item()))
+
+    def bytes_per_step(self) -> int:
+        """Algorithmic HBM bytes this rank moves per iteration: CSR stream + x once +
+        y write, then y read (sumsq), y read + x-slice write (scale)."""
+        a = self.A
+        rows = a.count
+        lo = min((b.col_min for b in a.blocks), default=0)
+        hi = max((b.col_max for b in a.blocks), default=-1)
+        x_read = max(0, hi - lo + 1)   # the columns this rank's rows touch (own slab + halo), not all of x
+        return a.nnz_local * 12 + (rows + len(a.blocks)) * 4 + x_read * 8 + rows * 8 + rows * 8 + rows * 16
+
+
+def _all_gather_slices(x, own, n, world, equal_split, group):
+    """Every rank's slice into every replica of x.  Equal slices: one in-place all-gather.  The
+    reference's rule gives the last block the remainder (src/mat_vec.cpp:245-246); collectives
+    want equal counts, so an uneven split falls back to one broadcast per owner."""
+    if equal_split:
+        dist.all_gather_into_tensor(x, own, group=group)
+        return
+    for r in range(world):
+        s, c = partition_rows(n, world, r)
+        dist.broadcast(x[s:s + c], src=r, group=group)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+# =========================================================================================
+def e2e_spmv_step(it: "PowerIteration", xh, yh):
+    """The distributed SpMV as a caller with HOST buffers sees it: this rank's slice of x comes
+    from pinned host memory, the replicas are refreshed (NCCL all-gather), y = A x, and this
+    rank's slice of y goes back to pinned host memory.  Returns after the copy has landed."""
+    A = it.A
+    own = it.x[A.start:A.start + A.count]
+    own.copy_(xh, non_blocking=True)
+    if it.world > 1:
+        _all_gather_slices(it.x, own, A.N, it.world, it.equal_split, it.group)
+    A.spmv(it.ops, it.x, it.y)
+    yh.copy_(it.y, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+
+def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler, with_e2e=True):
+    """Time `steps` power-iteration steps per x-refresh mode (device events, max over ranks)."""
+    from .lib import launch_count
+    ops = CudaOps(device)
+    A = PartitionedCSR.stencil27(n, rank, world, ops)
+    results = {}
+    for mode in modes:
+        try:
+            it = PowerIteration(A, ops, exchange=mode, overlap=overlap)
+        except Exception as e:  # e.g. symmetric memory not available on this box
+            results[mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            continue
+        for _ in range(max(3, warmup)):
+            it.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = launch_count()
+        with ClockSampler(device.index or 0) as clk:
+            e0.record()
+            for _ in range(steps):
+                it.step()
+            e1.record()
+            torch.cuda.synchronize()
+        launches = launch_count() - l0
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        results[mode] = {"ms_per_step": float(ms.item()), "norm": it.norm(), "launches": int(launches), "clocks": clk.summary(),
+                         "bytes_per_step_rank": it.bytes_per_step()}
+        if with_e2e and "e2e" not in results:
+            xh = torch.empty(A.count, dtype=torch.float64).pin_memory()
+            yh = torch.empty(A.count, dtype=torch.float64).pin_memory()
+            xh.copy_(it.x[A.start:A.start + A.count].cpu())
+            for _ in range(2):
+                e2e_spmv_step(it, xh, yh)
+            if world > 1:
+                dist.barrier()
+            k = max(3, min(steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_spmv_step(it, xh, yh)
+            dt = torch.tensor([(time.perf_counter() - t0) / k], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            results["e2e"] = {"ms_per_step": float(dt.item()) * 1e3, "h2d_bytes_per_step": A.count * 8 * world,
+                              "d2h_bytes_per_step": A.count * 8 * world}
+        del it
+        torch.cuda.empty_cache()
+    return A, results
+
+
+def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
+    """bench.py --gpus N under torchrun (one rank per GPU)."""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    n = args.grid
+    modes = [m for m in args.exchange.split(",") if m] if world > 1 else ["allgather"]
+    A, results = measure(n, rank, world, device, args.steps, args.warmup, modes, not args.no_overlap, ClockSampler)
+    if rank == 0:
+        primary = next(m for m in modes if "ms_per_step" in results.get(m, {}))
+        nnz_total = (3 * n - 2) ** 3
+        flops = 2.0 * nnz_total
+        r = results[primary]
+        ms = r["ms_per_step"]
+        peak, peak_kind = peak_hbm()
+        achieved = r["bytes_per_step_rank"] / (ms * 1e-3) / 1e9
+        e2e = results.get("e2e")
+        line = {
+            "metric": METRIC, "value": round(flops / (ms * 1e-3) / 1e9, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "row-partitioned fp64 CSR power iteration (SpMV + sum-of-squares all-reduce + normalise + x refresh), "
+                                   f"27-point stencil {n}^3 generated on device (BASELINE configs[4])",
+                       "rows": n ** 3, "nnz": nnz_total, "x_refresh": primary, "overlap": not args.no_overlap,
+                       "partition": f"equal row blocks x{world} (src/mat_vec.cpp:233)", "row_blocks_rank0": len(A.blocks),
+                       "cache": "per-rank inputs larger than L2 (126 MB)", "norm": r["norm"]},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "peak_source": peak_kind,
+                         "note": "rank 0's algorithmic HBM bytes of one whole iteration / iteration time"},
+            "e2e": ({"value": round(flops / (e2e["ms_per_step"] * 1e-3) / 1e9, 2), "unit": UNIT, "ms_per_step": round(e2e["ms_per_step"], 4),
+                     "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                     "call": "distributed y = A x: pinned x slices in, NCCL all-gather, SpMV, pinned y slices out"} if e2e else None),
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "x_refresh_modes": {m: ({"ms_per_step": round(v["ms_per_step"], 5), "gflops": round(flops / (v["ms_per_step"] * 1e-3) / 1e9, 2),
+                                     "norm": v["norm"]} if "ms_per_step" in v else v) for m, v in results.items() if m != "e2e"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

@@ -275,6 +275,23 @@ def run_single(args):
                         "frac": round(ell_bytes / (ell_ms * 1e-3) / 1e9 / peak, 4)}
         del E, ye
 
+    # ---- the iterated loop (power iteration) on one GPU: the denominator of the multi-GPU runs
+    if args.iterated_grid:
+        from arm_spmv_b200 import power
+        A.free_plan()
+        del A, x, y, yd, xh, yh
+        torch.cuda.empty_cache()
+        g = args.iterated_grid
+        Ap, res = power.measure(g, 0, 1, torch.device("cuda", 0), min(args.steps, 20), 3, ["allgather"], True, ClockSampler, with_e2e=False)
+        r = res["allgather"]
+        nnz_g = (3 * g - 2) ** 3
+        extra["iterated"] = {"workload": f"power iteration, 27-point stencil {g}^3 ({nnz_g} nnz, {len(Ap.blocks)} row blocks of < 2^31 entries), 1 GPU",
+                             "ms_per_step": round(r["ms_per_step"], 4), "gflops": round(2.0 * nnz_g / (r["ms_per_step"] * 1e-3) / 1e9, 2),
+                             "achieved_gbs": round(r["bytes_per_step_rank"] / (r["ms_per_step"] * 1e-3) / 1e9, 1),
+                             "frac": round(r["bytes_per_step_rank"] / (r["ms_per_step"] * 1e-3) / 1e9 / peak, 4), "norm": r["norm"]}
+        del Ap
+        torch.cuda.empty_cache()
+
     cpu = None
     if not args.no_cpu:
         gf, dt, kind, cores, sample = cpu_reference_arm(args.cpu_grid, args.cpu_reps)
@@ -320,6 +337,9 @@ def main():
     ap.add_argument("--no-ell", action="store_true")
     ap.add_argument("--cpu-grid", type=int, default=256)
     ap.add_argument("--cpu-reps", type=int, default=20)
+    ap.add_argument("--exchange", default="allgather,fused,halo", help="x refresh modes to time at N>1; the first that works is `value`")
+    ap.add_argument("--no-overlap", action="store_true", help="do not overlap interior rows with the x refresh")
+    ap.add_argument("--iterated-grid", type=int, default=512, help="N=1: also time the power-iteration loop on this grid (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.grid is None:

@@ -1,0 +1,138 @@
+"""Host-side logic of the row-partitioned power iteration on CPU: world_size 2 over gloo.
+
+The package has no CPU arithmetic; this test injects an `ops` object built on the oracle (test
+infrastructure) so that partitioning, the x refresh, the scalar all-reduce and the interior /
+boundary ordering run exactly as they do under torchrun on GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleOps:
+    device = torch.device("cpu")
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        pyoracle.build()
+        self.O = pyoracle.Oracle()
+
+    def empty(self, n):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def scalar(self):
+        return torch.zeros(1, dtype=torch.float64)
+
+    def init_x(self, x, seed):
+        x.copy_(torch.from_numpy(self.O.gen_vector(x.numel(), seed)))
+
+    def stencil_block(self, n, r0, r1):
+        rp, ci, va = self.O.gen_stencil27_csr(n, r0, r1)
+        return (r1 - r0, n ** 3, rp, ci, va), int(rp[-1])
+
+    def csr_block(self, nrow, ncol, row_ptr, col_ind, values):
+        return (nrow, ncol, row_ptr.numpy(), col_ind.numpy(), values.numpy()), int(col_ind.numel())
+
+    def spmv(self, payload, x, y):
+        nrow, ncol, rp, ci, va = payload
+        y.copy_(torch.from_numpy(self.O.csr_spmv(nrow, ncol, rp, ci, va, x.numpy(), np.zeros(nrow))))
+
+    def sumsq(self, y, out):
+        out[0] = self.O.dot(y.numpy(), y.numpy())
+
+    def scale_into(self, y, sumsq, x, offset, peer_ptrs=None):
+        # vec_axpby(1/nrm, y, 0, y, x_slice): the beta == 0 branch (src/vec_vec.cpp:46-53)
+        w = self.O.axpby(1.0 / np.sqrt(float(sumsq[0])), y.numpy(), 0.0, y.numpy())
+        x[offset:offset + y.numel()] = torch.from_numpy(w)
+
+    def col_range(self, payload):
+        ci = payload[3]
+        return (int(ci.min()), int(ci.max())) if len(ci) else (0, -1)
+
+
+def serial_power_iteration(O, n, steps, seed):
+    N = n ** 3
+    rp, ci, va = O.gen_stencil27_csr(n)
+    x = O.gen_vector(N, seed)
+    nrm = 0.0
+    for _ in range(steps):
+        y = O.csr_spmv(N, N, rp, ci, va, x, np.zeros(N))
+        nrm = np.sqrt(O.dot(y, y))
+        x = O.axpby(1.0 / nrm, y, 0.0, y)
+    return x, nrm
+
+
+def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arm_spmv_b200 import power
+        ops = OracleOps()
+        if generic:
+            rp, ci, va = ops.O.gen_stencil27_csr(n)
+            A = power.PartitionedCSR.from_csr(n ** 3, torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va), rank, world, ops)
+        else:
+            A = power.PartitionedCSR.stencil27(n, rank, world, ops, max_block_rows=50)
+        it = power.PowerIteration(A, ops, exchange=mode, overlap=overlap, seed=5)
+        for _ in range(steps):
+            it.step()
+        # after the last refresh every replica must hold the same, complete x
+        torch.save({"x": it.x.clone(), "norm": it.norm(), "start": A.start, "count": A.count,
+                    "blocks": [(b.row0, b.nrow, b.boundary) for b in A.blocks]}, f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,overlap,generic", [(2, 6, True, False), (2, 7, False, False), (3, 5, True, False), (2, 6, True, True)])
+def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, overlap, generic):
+    steps = 4
+    port = 29500 + (os.getpid() + world * 7 + n) % 400
+    out = str(tmp_path / "res")
+    mp.spawn(_worker, args=(world, port, n, steps, "allgather", overlap, generic, out), nprocs=world, join=True)
+    x_ref, nrm_ref = serial_power_iteration(oracle, n, steps, 5)
+    covered = 0
+    for r in range(world):
+        res = torch.load(f"{out}.{r}")
+        assert res["start"] == covered
+        covered += res["count"]
+        # rows are multiplied in the reference's order, so only the norm (a sum over ranks) differs in rounding
+        assert np.max(np.abs(res["x"].numpy() - x_ref)) <= 1e-13
+        assert abs(res["norm"] - nrm_ref) <= 1e-12 * nrm_ref
+        rows = sum(b[1] for b in res["blocks"])
+        assert rows == res["count"]
+    assert covered == n ** 3
+
+
+def test_stencil_row_blocks_cover_and_flag_boundaries(oracle):
+    sys.path.insert(0, ROOT)
+    from arm_spmv_b200 import power
+    for n, world in [(6, 2), (5, 3), (8, 4), (4, 4), (9, 8)]:
+        N = n ** 3
+        rp, ci, _ = oracle.gen_stencil27_csr(n)
+        for rank in range(world):
+            start, count = power.partition_rows(N, world, rank)
+            pieces = power.stencil_row_blocks(n, start, count, world, max_rows=40)
+            at = start
+            for r0, r1, bnd in sorted(pieces):
+                assert r0 == at and r1 > r0
+                at = r1
+                cols = ci[rp[r0]:rp[r1]]
+                needs_remote = cols.min() < start or cols.max() >= start + count
+                assert bnd or not needs_remote, (n, world, rank, r0, r1)   # interior pieces never read remote x
+            assert at == start + count
+
+
+def test_partition_matches_reference_rule(oracle):
+    sys.path.insert(0, ROOT)
+    from arm_spmv_b200 import power
+    for n, parts in [(10, 3), (64, 8), (7, 7), (5, 8)]:
+        for p in range(parts):
+            assert power.partition_rows(n, parts, p) == oracle.partition(n, parts, p)
