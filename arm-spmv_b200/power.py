@@ -16,6 +16,8 @@ x refresh modes
   allgather  NCCL all-gather of every slice into every replica (the north star's wording).
   fused      the scale kernel stores each normalised value straight into all replicas through
              NVLink peer pointers (torch symmetric memory): compute + "all-gather" in one kernel.
+  push       the scale kernel writes the local replica only (critical path); a second kernel on the
+             side stream stores that slice into the other replicas while interior rows are multiplied.
   halo       column-footprint analysis: a block only needs x over [min col, max col] of its rows;
              only the parts of that range owned by other ranks are pulled.
 With `overlap`, rows whose columns all fall inside the own slice (interior) are multiplied while
@@ -117,6 +119,13 @@ class CudaOps:
         """y = A_block x (overwrite: saves Fill(0) and the read of y)."""
         self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
 
+    def reserve_sms(self, payload, reserve):
+        """Run this block's persistent SpMV on (SMs - reserve) CTAs so that a collective launched on
+        another stream finds free SMs instead of queueing behind the persistent kernel."""
+        n = C.c_int(0)
+        self.check(self.lib.thsp_sm_count(C.byref(n)))
+        self.check(self.lib.thsp_csr_plan_set_stream_config(payload.plan(), 0, 0, 0, max(1, n.value - reserve)))
+
     def sumsq(self, y, out):
         self.check(self.lib.thsp_sumsq_dev_f64(C.c_int64(y.numel()), self.ptr(y), self.ptr(out), self.stream()))
 
@@ -187,13 +196,22 @@ class PartitionedCSR:
 
 
 class PowerIteration:
-    def __init__(self, A: PartitionedCSR, ops, exchange: str = "allgather", overlap: bool = True, group=None, seed: int = 11):
+    def __init__(self, A: PartitionedCSR, ops, exchange: str = "allgather", overlap: bool = True, group=None, seed: int = 11,
+                 reserve_sms: int = 16):
         self.A, self.ops, self.exchange, self.overlap, self.group = A, ops, exchange, overlap, group
         self.world, self.rank = A.world, A.rank
+        if hasattr(ops, "reserve_sms"):
+            for b in A.blocks:   # interior blocks run next to the x refresh; boundary blocks run alone
+                # Only the NCCL all-gather needs whole SMs (its CTAs do not fit beside the persistent
+                # SpMV CTA); the push / halo / barrier kernels are small enough to co-reside.
+                # Measured on 2 GPUs (profiles/r01_power_2gpu.txt): all-gather 5.23 -> 4.43 ms with 16
+                # SMs left free, while push/halo lose ~5 % when SMs are taken away.
+                free = reserve_sms if (self.world > 1 and overlap and not b.boundary and exchange == "allgather") else 0
+                ops.reserve_sms(b.payload, free)
         self.y = ops.empty(A.count)
         self.ss = ops.scalar()
         self.symm = None
-        if self.world > 1 and exchange in ("fused", "halo"):
+        if self.world > 1 and exchange in ("fused", "push", "halo"):
             import torch.distributed._symmetric_memory as symm_mem
             self.x = symm_mem.empty(A.N, dtype=torch.float64, device=ops.device)
             self.symm = symm_mem.rendezvous(self.x, group=dist.group.WORLD.group_name if group is None else group.group_name)
@@ -252,6 +270,9 @@ class PowerIteration:
         if self.exchange == "halo":
             self._barrier_async(cur, pull=True)
             return
+        if self.exchange == "push":
+            self._barrier_async(cur, push=True)
+            return
         # NCCL all-gather of the slices, in place, on the side stream
         done = torch.cuda.Event() if cur is not None else None
         if cur is not None:
@@ -265,13 +286,22 @@ class PowerIteration:
                 self.x_ready = torch.cuda.Event()
                 self.x_ready.record(self.comm_stream)
 
-    def _barrier_async(self, cur, pull=False):
-        """Symmetric-memory barrier on the side stream (and, for `halo`, the pulls of the needed
-        pieces of x from their owners' replicas), so interior rows can start meanwhile."""
+    def _barrier_async(self, cur, pull=False, push=False):
+        """Side-stream part of the refresh, so that interior rows can be multiplied meanwhile:
+        `push`: store the own (already normalised) slice into every other replica over NVLink with
+        one kernel, then a symmetric-memory barrier; `halo`: barrier, then pull the needed pieces
+        of x from their owners' replicas; `fused`: just the barrier."""
         done = torch.cuda.Event()
         done.record(cur)
         self.comm_stream.wait_event(done)
         with torch.cuda.stream(self.comm_stream):
+            if push:
+                A = self.A
+                if not hasattr(self, "_one"):
+                    self._one = torch.ones(1, dtype=torch.float64, device=self.x.device)
+                others = [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
+                own = self.x[A.start:A.start + A.count]
+                self.ops.scale_into(own, self._one, self.x, A.start, peer_ptrs=others)   # x * (1/sqrt(1)) == x exactly
             self.symm.barrier()
             if pull:
                 for owner, lo, hi in self.A.needed_ranges():
@@ -332,7 +362,7 @@ def e2e_spmv_step(it: "PowerIteration", xh, yh):
     torch.cuda.current_stream().synchronize()
 
 
-def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler, with_e2e=True):
+def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler, with_e2e=True, reserve_sms=16):
     """Time `steps` power-iteration steps per x-refresh mode (device events, max over ranks)."""
     from .lib import launch_count
     ops = CudaOps(device)
@@ -340,7 +370,7 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
     results = {}
     for mode in modes:
         try:
-            it = PowerIteration(A, ops, exchange=mode, overlap=overlap)
+            it = PowerIteration(A, ops, exchange=mode, overlap=overlap, reserve_sms=reserve_sms)
         except Exception as e:  # e.g. symmetric memory not available on this box
             results[mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
             continue
@@ -398,7 +428,8 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
         dist.init_process_group("nccl", device_id=device)
     n = args.grid
     modes = [m for m in args.exchange.split(",") if m] if world > 1 else ["allgather"]
-    A, results = measure(n, rank, world, device, args.steps, args.warmup, modes, not args.no_overlap, ClockSampler)
+    A, results = measure(n, rank, world, device, args.steps, args.warmup, modes, not args.no_overlap, ClockSampler,
+                         reserve_sms=args.reserve_sms)
     if rank == 0:
         primary = next(m for m in modes if "ms_per_step" in results.get(m, {}))
         nnz_total = (3 * n - 2) ** 3
@@ -414,7 +445,7 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "row-partitioned fp64 CSR power iteration (SpMV + sum-of-squares all-reduce + normalise + x refresh), "
                                    f"27-point stencil {n}^3 generated on device (BASELINE configs[4])",
-                       "rows": n ** 3, "nnz": nnz_total, "x_refresh": primary, "overlap": not args.no_overlap,
+                       "rows": n ** 3, "nnz": nnz_total, "x_refresh": primary, "overlap": not args.no_overlap, "sms_reserved_for_refresh": args.reserve_sms,
                        "partition": f"equal row blocks x{world} (src/mat_vec.cpp:233)", "row_blocks_rank0": len(A.blocks),
                        "cache": "per-rank inputs larger than L2 (126 MB)", "norm": r["norm"]},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
