@@ -427,6 +427,10 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
     n = args.grid
+    if args.reserve_sms < 0:
+        # NCCL's all-gather wants more CTAs the more peers it talks to: measured best 16 SMs at 2 GPUs,
+        # 48 at 8 (profiles/r01_power_8gpu.txt)
+        args.reserve_sms = 16 * max(1, int(math.log2(max(world, 2))))
     modes = [m for m in args.exchange.split(",") if m] if world > 1 else ["allgather"]
     A, results = measure(n, rank, world, device, args.steps, args.warmup, modes, not args.no_overlap, ClockSampler,
                          reserve_sms=args.reserve_sms)
