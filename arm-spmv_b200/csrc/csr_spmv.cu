@@ -24,6 +24,7 @@
 //
 // The plan picks kernel and L from the row-length histogram (thsp_csr_plan_create).
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -483,11 +484,46 @@ __global__ void row_hist_kernel(int nrow, const int* __restrict__ row_ptr, unsig
     if (threadIdx.x == 0) atomicMax(max_len, mx);
 }
 
+__global__ void __launch_bounds__(256) chunk_footprint_kernel(const int* __restrict__ chunk_row0, const int* __restrict__ row_ptr,
+                                                              const int* __restrict__ col, int* __restrict__ cmin, int* __restrict__ cmax)
+{
+    // grid = (parts, chunks): min / max column over the entries of row chunk blockIdx.y
+    const int c = blockIdx.y;
+    const int e0 = row_ptr[chunk_row0[c]], e1 = row_ptr[chunk_row0[c + 1]];
+    int lo = 0x7fffffff, hi = -1;
+    for (int e = e0 + blockIdx.x * 256 + threadIdx.x; e < e1; e += gridDim.x * 256) {
+        const int v = ld_stream(col + e);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= 0) {
+        atomicMin(cmin + c, lo);
+        atomicMax(cmax + c, hi);
+    }
+}
+
 }  // namespace thsp
 
 using namespace thsp;
 
+// Row chunks + column footprints for the host-buffer path (thsp_csr_plan_spmv_host_f64):
+// chunk c needs x only over [cmin[c], cmax[c]], so its SpMV can start as soon as that range has
+// arrived over PCIe, and its slice of y can leave while later chunks are still being multiplied.
+struct HostPipe {
+    int nchunks = 0;
+    std::vector<int> row0, cmin, cmax;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t begin = nullptr;
+    std::vector<cudaEvent_t> in_done, k_done;
+};
+
 struct thsp_csr_plan {
+    HostPipe* pipe = nullptr;
     int nrow, ncol, nnz, value_bytes;
     const int* row_ptr;
     const int* col_ind;
@@ -626,6 +662,15 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
 
 int thsp_csr_plan_destroy(thsp_csr_plan* plan)
 {
+    if (plan && plan->pipe) {
+        HostPipe* hp = plan->pipe;
+        for (auto e : hp->in_done) cudaEventDestroy(e);
+        for (auto e : hp->k_done) cudaEventDestroy(e);
+        if (hp->begin) cudaEventDestroy(hp->begin);
+        if (hp->s_in) cudaStreamDestroy(hp->s_in);
+        if (hp->s_out) cudaStreamDestroy(hp->s_out);
+        delete hp;
+    }
     delete plan;
     return 0;
 }
@@ -672,16 +717,96 @@ int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, 
     return plan_spmv<float>(plan, x, y, accumulate, as_stream(stream));
 }
 
-int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host, double* x_dev,
+static int build_host_pipe(thsp_csr_plan* p, cudaStream_t s)
+{
+    HostPipe* hp = new HostPipe();
+    // ~1M rows per chunk, at most 32 chunks; a single chunk for small matrices or the merge kernel
+    int n = p->kernel == THSP_CSR_MERGE ? 1 : std::min(32, std::max(1, p->nrow / (1 << 20)));
+    hp->nchunks = n;
+    hp->row0.resize(n + 1);
+    for (int c = 0; c <= n; ++c) hp->row0[c] = (int)((int64_t)p->nrow * c / n / 32 * 32);
+    hp->row0[n] = p->nrow;
+    hp->cmin.assign(n, 0x7fffffff);
+    hp->cmax.assign(n, -1);
+    int* d = static_cast<int*>(scratch(sizeof(int) * (3 * (size_t)n + 1), 4));
+    if (!d) { delete hp; return 1; }
+    THSP_CUDA(cudaMemcpyAsync(d, hp->row0.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    THSP_CUDA(cudaMemcpyAsync(d + n + 1, hp->cmin.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    THSP_CUDA(cudaMemcpyAsync(d + 2 * n + 1, hp->cmax.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    chunk_footprint_kernel<<<dim3(64, n), 256, 0, s>>>(d, p->row_ptr, p->col_ind, d + n + 1, d + 2 * n + 1);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaMemcpyAsync(hp->cmin.data(), d + n + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaMemcpyAsync(hp->cmax.data(), d + 2 * n + 1, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    THSP_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+    THSP_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+    THSP_CUDA(cudaEventCreateWithFlags(&hp->begin, cudaEventDisableTiming));
+    hp->in_done.resize(n);
+    hp->k_done.resize(n);
+    for (int c = 0; c < n; ++c) {
+        THSP_CUDA(cudaEventCreateWithFlags(&hp->in_done[c], cudaEventDisableTiming));
+        THSP_CUDA(cudaEventCreateWithFlags(&hp->k_done[c], cudaEventDisableTiming));
+    }
+    p->pipe = hp;
+    return 0;
+}
+
+// Host x in, host y out.  Three streams: x pieces arrive on s_in in the order the row chunks need
+// them, each chunk is multiplied on the caller's stream as soon as its column range is there, its
+// rows of y leave on s_out while the next chunk runs.  PCIe is full duplex, so for banded
+// matrices the call costs about one transfer of x plus one chunk, not x + SpMV + y in sequence.
+int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host, double* y_host, double* x_dev,
                                 double* y_dev, int accumulate, thsp_stream_t stream)
 {
-    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
+    THSP_REQUIRE(cplan != nullptr && cplan->value_bytes == 8, "plan is null or not fp64");
+    thsp_csr_plan* plan = const_cast<thsp_csr_plan*>(cplan);
     cudaStream_t s = as_stream(stream);
-    THSP_CUDA(cudaMemcpyAsync(x_dev, x_host, sizeof(double) * (size_t)plan->ncol, cudaMemcpyHostToDevice, s));
-    if (accumulate)
-        THSP_CUDA(cudaMemcpyAsync(y_dev, y_host, sizeof(double) * (size_t)plan->nrow, cudaMemcpyHostToDevice, s));
-    if (plan_spmv<double>(plan, x_dev, y_dev, accumulate, s)) return 1;
-    THSP_CUDA(cudaMemcpyAsync(y_host, y_dev, sizeof(double) * (size_t)plan->nrow, cudaMemcpyDeviceToHost, s));
+    if (plan->nrow <= 0) return 0;
+    if (!plan->pipe && build_host_pipe(plan, s)) return 1;
+    HostPipe* hp = plan->pipe;
+    const double* val = static_cast<const double*>(plan->val);
+    THSP_CUDA(cudaEventRecord(hp->begin, s));          // earlier work on the scratch buffers
+    THSP_CUDA(cudaStreamWaitEvent(hp->s_in, hp->begin, 0));
+    THSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->begin, 0));
+    int lo = 0, hi = 0;   // x[lo, hi) has been queued for upload
+    bool any = false;
+    for (int c = 0; c < hp->nchunks; ++c) {
+        const int r0 = hp->row0[c], r1 = hp->row0[c + 1];
+        if (r1 <= r0) continue;
+        if (hp->cmax[c] >= hp->cmin[c]) {
+            const int a = hp->cmin[c], b = hp->cmax[c] + 1;
+            if (!any) {
+                THSP_CUDA(cudaMemcpyAsync(x_dev + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, hp->s_in));
+                lo = a; hi = b; any = true;
+            } else {
+                if (a < lo) {
+                    THSP_CUDA(cudaMemcpyAsync(x_dev + a, x_host + a, sizeof(double) * (size_t)(lo - a), cudaMemcpyHostToDevice, hp->s_in));
+                    lo = a;
+                }
+                if (b > hi) {
+                    THSP_CUDA(cudaMemcpyAsync(x_dev + hi, x_host + hi, sizeof(double) * (size_t)(b - hi), cudaMemcpyHostToDevice, hp->s_in));
+                    hi = b;
+                }
+            }
+        }
+        if (accumulate)
+            THSP_CUDA(cudaMemcpyAsync(y_dev + r0, y_host + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyHostToDevice, hp->s_in));
+        THSP_CUDA(cudaEventRecord(hp->in_done[c], hp->s_in));
+        THSP_CUDA(cudaStreamWaitEvent(s, hp->in_done[c], 0));
+        int rc;
+        if (hp->nchunks == 1) rc = plan_spmv<double>(plan, x_dev, y_dev, accumulate, s);
+        else if (plan->kernel == THSP_CSR_STREAM)
+            rc = run_stream<double>(plan->stream_cfg, plan->ctas, r1 - r0, plan->nnz, plan->row_ptr + r0, plan->col_ind, val, x_dev,
+                                    y_dev + r0, accumulate, s);
+        else
+            rc = run_vector<double>(plan->kernel == THSP_CSR_SCALAR ? 1 : plan->lanes, r1 - r0, plan->row_ptr + r0, plan->col_ind, val,
+                                    x_dev, y_dev + r0, accumulate, s);
+        if (rc) return rc;
+        THSP_CUDA(cudaEventRecord(hp->k_done[c], s));
+        THSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->k_done[c], 0));
+        THSP_CUDA(cudaMemcpyAsync(y_host + r0, y_dev + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, hp->s_out));
+    }
+    THSP_CUDA(cudaStreamSynchronize(hp->s_out));
     THSP_CUDA(cudaStreamSynchronize(s));
     return 0;
 }

@@ -201,3 +201,31 @@ def test_coo_sorted_uses_carry(thsp, cuda, oracle):
     Y = H.Vector(np.zeros(nrow)); H.COOMatirxMatVector(H.COOMatrix(nrow, nrow, ri, ci, va), H.Vector(x), Y)
     ref = oracle.csr_spmv(nrow, nrow, rp, ci, va, x, np.zeros(nrow))
     assert max_row_error(host(Y.values), ref, row_scale_csr(nrow, rp, ci, va, x)) <= TOL64
+
+
+@pytest.mark.parametrize("which,accumulate", [("stencil128", False), ("stencil128", True), ("uniform_big", False), ("tiny", True)])
+def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
+    """thsp_csr_plan_spmv_host_f64: pinned x in, y out, row chunks pipelined over three streams.
+    Must equal the device path bit for bit (same kernels, same per-row order)."""
+    import ctypes
+    from arm_spmv_b200 import host as H
+    if which == "stencil128":      # 2.1 M rows -> 2 chunks, banded footprints
+        rp, ci, va = oracle.gen_stencil27_csr(128); nrow = ncol = 128 ** 3
+    elif which == "uniform_big":   # 3.2 M rows -> 3 chunks, every chunk needs all of x
+        nrow = ncol = 3_200_000
+        ri, cj, v = oracle.gen_uniform_coo(nrow, ncol, 12_000_000, 43)
+        rp, ci, va, _ = oracle.coo2csr(nrow, ncol, ri, cj, v)
+    else:
+        rp, ci, va = oracle.gen_stencil27_csr(7); nrow = ncol = 343
+    A = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=dev(rp), col_ind=dev(ci), values=dev(va))
+    x = oracle.gen_vector(ncol, 21); y0 = oracle.gen_vector(nrow, 22) - 0.5
+    xh = torch.from_numpy(x).pin_memory(); yh = torch.from_numpy(y0.copy()).pin_memory()
+    xd = torch.full((ncol,), float("nan"), dtype=torch.float64, device="cuda")
+    yd = torch.full((nrow,), float("nan"), dtype=torch.float64, device="cuda")
+    lib = thsp.load()
+    for _ in range(2):   # twice: the second call reuses the pipeline built by the first
+        yh.copy_(torch.from_numpy(y0))
+        thsp.lib.check(lib.thsp_csr_plan_spmv_host_f64(A.plan(), ctypes.c_void_p(xh.data_ptr()), ctypes.c_void_p(yh.data_ptr()),
+                                                       thsp.lib.ptr(xd), thsp.lib.ptr(yd), 1 if accumulate else 0, thsp.lib.current_stream()))
+        ref = oracle.csr_spmv(nrow, ncol, rp, ci, va, x, y0 if accumulate else np.zeros(nrow))
+        assert_bits(yh.numpy(), ref, f"host path {which} acc={accumulate}")
