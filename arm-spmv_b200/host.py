@@ -130,8 +130,9 @@ class CSRMatrix:
     def nnz(self):
         return self.col_ind.numel()
 
-    def plan(self):
-        """Row-length histogram -> kernel choice; cached until the arrays are replaced."""
+    def plan(self, autotune: bool = False):
+        """Row-length histogram -> kernel choice (or a measurement when autotune=True or
+        THSP_AUTOTUNE=1); cached until the arrays are replaced."""
         key = (self.row_ptr.data_ptr(), self.col_ind.data_ptr(), self.values.data_ptr(), self.nrow, self.nnz)
         if self._plan is None or self._plan[0] != key:
             self.free_plan()
@@ -139,6 +140,9 @@ class CSRMatrix:
             check(load().thsp_csr_plan_create(C.byref(h), self.nrow, self.ncol, self.nnz, ptr(self.row_ptr), ptr(self.col_ind),
                                               ptr(self.values), self.values.element_size(), current_stream()))
             self._plan = (key, h)
+            import os
+            if autotune or os.environ.get("THSP_AUTOTUNE") == "1":
+                check(load().thsp_csr_plan_autotune(h, current_stream()))
         return self._plan[1]
 
     def plan_kernel(self):

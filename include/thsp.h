@@ -104,6 +104,9 @@ THSP_API int thsp_csr_plan_set_kernel(thsp_csr_plan* plan, int kernel, int lanes
 /* Tuning knobs of the STREAM kernel (0 keeps the current value): warps per CTA, ring depth per
  * warp, entries per stage (multiple of 4), number of persistent CTAs. */
 THSP_API int thsp_csr_plan_set_stream_config(thsp_csr_plan* plan, int warps, int stages, int chunk, int ctas);
+/* Replace the heuristic choice by a measurement: times every applicable kernel on this matrix
+ * (scratch vectors, ~20 SpMVs) and keeps the fastest.  Synchronous. */
+THSP_API int thsp_csr_plan_autotune(thsp_csr_plan* plan, thsp_stream_t stream);
 /* histogram[b] = number of rows whose length l satisfies: b=0: l==0; b>=1: 2^(b-1) <= l < 2^b  (32 bins) */
 THSP_API int thsp_csr_plan_histogram(const thsp_csr_plan* plan, int64_t* histogram32, int* max_row_len);
 THSP_API int thsp_csr_plan_spmv_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate,

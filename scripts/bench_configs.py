@@ -53,6 +53,8 @@ def spmv_all(A, name, ell=True, dia=False, kernels=()):
     csr_b = nnz * 12 + (nrow + 1) * 4 + ncol * 8 + 2 * nrow * 8
     print(f"   plan picks: {B.plan_kernel()}")
     ms = timeit(lambda: H.CSRMatrixMatVector(B, x, y)); report(f"{name}: CSR auto {B.plan_kernel()}", ms, csr_b, fl)
+    check(lib.thsp_csr_plan_autotune(B.plan(), current_stream()))
+    ms = timeit(lambda: H.CSRMatrixMatVector(B, x, y)); report(f"{name}: CSR autotuned {B.plan_kernel()}", ms, csr_b, fl)
     for kid, lanes, kn in kernels:
         ms = timeit(lambda: H.csr_spmv_kernel(kid, lanes, B, x.values, y.values, True)); report(f"{name}: CSR {kn}", ms, csr_b, fl)
     ms = timeit(lambda: H.COOMatirxMatVector(A, x, y)); report(f"{name}: COO", ms, nnz * 16 + ncol * 8 + 2 * nrow * 8, fl)
@@ -86,5 +88,7 @@ for w in which:
         spmv_all(H.rmat_coo(24, 16 << 24, 42), "rmat s24", ell=False, kernels=[(V, 8, "vector8"), (V, 16, "vector16"), (V, 32, "vector32"), (ST, 1, "stream"), (MG, 1, "merge")])
     elif w == "uniform":  # configs[3]: uniform 8M x 8M, 128M entries
         spmv_all(H.uniform_coo(1 << 23, 1 << 23, 1 << 27, 43), "uniform 8M", ell=True, kernels=[(V, 8, "vector8"), (V, 16, "vector16"), (ST, 1, "stream"), (MG, 1, "merge")])
+    elif w == "lap5big":
+        spmv_all(H.lap5_coo(4096), "lap5 4096^2", dia=True, kernels=[(1, 1, "scalar"), (V, 2, "vector2"), (V, 4, "vector4"), (ST, 1, "stream")])
     elif w == "stencil":
         spmv_all(H.stencil27_coo(256), "stencil 256^3", dia=True, kernels=[(V, 8, "vector8"), (V, 16, "vector16"), (V, 32, "vector32"), (MG, 1, "merge")])
