@@ -155,7 +155,16 @@ __global__ void __launch_bounds__(256) hist_kernel(int n, const int* __restrict_
 }
 
 // ================================================================== LSD radix sort ========
+// One pass = digit histogram per CTA tile -> exclusive scan over (digit-major, tile-minor) counts
+// -> stable scatter.  A tile is 4096 consecutive elements; warp w owns elements
+// [w*512, (w+1)*512) of it and walks them in 16 rounds of 32 (coalesced loads).
+// Stable rank of an element = (elements with the same digit earlier in the tile): inside a warp
+// it comes from __match_any_sync against a warp-private running counter in shared memory (no CTA
+// barrier per round), across warps from one prefix over the eight warp counters per digit.
+// Elements are then placed in shared memory in sorted order and written out so that consecutive
+// threads write consecutive addresses of a digit run.
 static constexpr int kRadixThreads = 256;
+static constexpr int kRadixWarps = kRadixThreads / 32;
 static constexpr int kRadixRounds = 16;
 static constexpr int kRadixTile = kRadixThreads * kRadixRounds;  // 4096 keys per CTA
 
@@ -163,13 +172,17 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(int n, const 
                                                                    int* __restrict__ counts, int nblk)
 {
     __shared__ int h[256];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     h[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * kRadixTile;
 #pragma unroll 4
     for (int r = 0; r < kRadixRounds; ++r) {
         const int k = base + r * kRadixThreads + threadIdx.x;
-        if (k < n) atomicAdd(&h[(ld_stream(key + k) >> shift) & 255], 1);
+        const int d = k < n ? ((ld_stream(key + k) >> shift) & 255) : 256 + lane;
+        const unsigned peers = __match_any_sync(full, d);          // one atomic per distinct digit in the warp
+        if (k < n && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&h[d], __popc(peers));
     }
     __syncthreads();
     counts[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
@@ -181,42 +194,74 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
                                                                       const int* __restrict__ offsets, int nblk,
                                                                       int* __restrict__ key_out, int* __restrict__ idx_out)
 {
-    __shared__ int base[256];
-    __shared__ int wcnt[kRadixThreads / 32][256];
+    __shared__ int wcnt[kRadixWarps][256];   // per-warp digit counters, later exclusive warp offsets
+    __shared__ int tile_off[256];            // first position of each digit inside the sorted tile
+    __shared__ int gbase[256];               // where this tile's run of each digit starts in the output
+    __shared__ int s_key[kRadixTile];
+    __shared__ int s_idx[kRadixTile];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    base[threadIdx.x] = offsets[threadIdx.x * nblk + blockIdx.x];
     const int tile = blockIdx.x * kRadixTile;
+    const int tile_n = min(kRadixTile, n - tile);
+#pragma unroll
+    for (int i = 0; i < kRadixWarps; ++i) wcnt[i][threadIdx.x] = 0;
+    gbase[threadIdx.x] = offsets[threadIdx.x * nblk + blockIdx.x];
+    __syncthreads();
+
+    int kv[kRadixRounds], iv[kRadixRounds], rk[kRadixRounds];  // key, index, rank inside the warp's segment
+#pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
+        const int e = w * (32 * kRadixRounds) + r * 32 + lane;   // position inside the tile
+        const bool ok = e < tile_n;
+        kv[r] = ok ? key_in[tile + e] : 0;
+        iv[r] = ok ? (idx_in ? idx_in[tile + e] : tile + e) : 0;
+    }
 #pragma unroll
-        for (int i = 0; i < kRadixThreads / 32; ++i) wcnt[i][threadIdx.x] = 0;
-        __syncthreads();
-        const int k = tile + r * kRadixThreads + threadIdx.x;
-        const bool ok = k < n;
-        const int kv = ok ? key_in[k] : 0;
-        const int iv = ok ? (idx_in ? idx_in[k] : k) : 0;
-        const int d = ok ? ((kv >> shift) & 255) : 256 + lane;  // invalid lanes never match anyone
+    for (int r = 0; r < kRadixRounds; ++r) {
+        const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+        const bool ok = e < tile_n;
+        const int d = ok ? ((kv[r] >> shift) & 255) : 256 + lane;  // invalid lanes match nobody
         const unsigned peers = __match_any_sync(full, d);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        if (ok && rank == 0) wcnt[w][d] = __popc(peers);
-        __syncthreads();
-        {
-            int run = base[threadIdx.x];
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        int base = 0;
+        if (ok) base = wcnt[w][d];
+        __syncwarp();
+        if (ok && before == 0) wcnt[w][d] = base + __popc(peers);
+        __syncwarp();
+        rk[r] = base + before;
+    }
+    __syncthreads();
+    {   // thread d: exclusive prefix of digit d over the warps, and the digit's total in the tile
+        const int d = threadIdx.x;
+        int run = 0;
 #pragma unroll
-            for (int i = 0; i < kRadixThreads / 32; ++i) {
-                const int c = wcnt[i][threadIdx.x];
-                wcnt[i][threadIdx.x] = run;
-                run += c;
-            }
-            base[threadIdx.x] = run;
+        for (int i = 0; i < kRadixWarps; ++i) {
+            const int c = wcnt[i][d];
+            wcnt[i][d] = run;
+            run += c;
         }
-        __syncthreads();
-        if (ok) {
-            const int pos = wcnt[w][d] + rank;
-            key_out[pos] = kv;
-            idx_out[pos] = iv;
+        int tot;
+        const int excl = block_exclusive_scan(run, &tot);   // exclusive scan over digits
+        tile_off[d] = excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; ++r) {
+        const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+        if (e < tile_n) {
+            const int d = (kv[r] >> shift) & 255;
+            const int pos = tile_off[d] + wcnt[w][d] + rk[r];
+            s_key[pos] = kv[r];
+            s_idx[pos] = iv[r];
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tile_n; t += kRadixThreads) {
+        const int k = s_key[t];
+        const int d = (k >> shift) & 255;
+        const int out = gbase[d] + (t - tile_off[d]);
+        key_out[out] = k;
+        idx_out[out] = s_idx[t];
     }
 }
 

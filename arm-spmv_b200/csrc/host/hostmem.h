@@ -30,12 +30,21 @@ inline T* alloc(size_t n)
 // 0 plain host, 1 device, 2 managed, 3 pinned host
 inline int kind(const void* p) { return p ? thsp_pointer_kind(p) : 0; }
 
+// Managed arrays are prefetched to the GPU the first time a kernel is about to read them and
+// not again: cudaMemPrefetchAsync on resident pages still walks the range (measured ~1 ms per
+// 20 MB), which would dominate a 13 us SpMV.  If host code writes into such an array later, its
+// pages migrate back on the CPU fault and return to the GPU on the next kernel's page faults.
+bool first_gpu_use(const void* p);
+void prefetch_traced(const void* p, size_t bytes);   // prefetch to the GPU; THSP_TRACE=1 prints how long it took
+void forget_gpu_use(const void* p);
+
 // Release an array owned by one of the API classes, whichever way it was obtained.
 template <class T>
 inline void release(T*& p)
 {
     if (!p) return;
     const int k = kind(p);
+    forget_gpu_use(p);
     if (k == 1 || k == 2) ok(thsp_free(p), "cudaFree");
     else if (k == 3) ok(thsp_free_host(p), "cudaFreeHost");
     else delete[] p;
@@ -55,7 +64,7 @@ public:
         const int k = kind(p);
         if (k == 1 || k == 2 || n == 0) {
             dev_ = host_;
-            if (k == 2 && prefetch && n) ok(thsp_prefetch(p, n * sizeof(T), 1, nullptr), "prefetch");
+            if (k == 2 && n && first_gpu_use(p) && prefetch) prefetch_traced(p, n * sizeof(T));
         } else {
             void* d = nullptr;
             ok(thsp_malloc(&d, n * sizeof(T)), "staging allocation");
@@ -103,7 +112,9 @@ inline void copy(T* dst, const T* src, size_t n)
 int peek_int(const int* p);
 
 // CSR plan cache (kernel choice from the row-length histogram), keyed by the matrix arrays.
-thsp_csr_plan* csr_plan(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const double* val);
+// nnz < 0: look the matrix up by its arrays alone (a hit also returns the entry count through
+// *nnz_out, saving the device read of row_ptr[nrow]); returns nullptr on a miss.
+thsp_csr_plan* csr_plan(int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind, const double* val, int* nnz_out = nullptr);
 void forget_plans(const void* any_array);
 
 }  // namespace thsp_host

@@ -33,17 +33,26 @@ void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y)
 void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y)
 {
     if (A.nrow <= 0) return;
-    const int nnz = peek_int(A.row_ptr + A.nrow);
     const int k = kind(A.values);
     View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
     if (k == 1 || k == 2) {
         // Library-owned (managed) arrays: the plan remembers the kernel chosen from the row-length
-        // histogram; its creation also brings the matrix into HBM.
-        const bool known = false;
-        (void)known;
-        thsp_csr_plan* plan = csr_plan(A.nrow, A.ncol, nnz, A.row_ptr, A.col_ind, A.values);
+        // histogram and the entry count; creating it also brings the matrix into HBM.  Plans are
+        // dropped when the matrix is freed or reassigned (CSRMatrix::Free).
+        int nnz = 0;
+        thsp_csr_plan* plan = csr_plan(A.nrow, A.ncol, -1, A.row_ptr, A.col_ind, A.values, &nnz);
+        if (!plan) {
+            nnz = peek_int(A.row_ptr + A.nrow);
+            if (k == 2) {
+                if (first_gpu_use(A.row_ptr)) prefetch_traced(A.row_ptr, sizeof(int) * ((size_t)A.nrow + 1));
+                if (nnz && first_gpu_use(A.col_ind)) prefetch_traced(A.col_ind, sizeof(int) * (size_t)nnz);
+                if (nnz && first_gpu_use(A.values)) prefetch_traced(A.values, sizeof(double) * (size_t)nnz);
+            }
+            plan = csr_plan(A.nrow, A.ncol, nnz, A.row_ptr, A.col_ind, A.values);
+        }
         ok(thsp_csr_plan_spmv_f64(plan, xv, yv, 1, nullptr), "CSR SpMV");
     } else {
+        const int nnz = peek_int(A.row_ptr + A.nrow);
         View<int> rp(A.row_ptr, (size_t)A.nrow + 1, false), ci(A.col_ind, nnz, false);
         View<double> va(A.values, nnz, false);
         ok(thsp_csr_spmv_f64(A.nrow, A.ncol, nnz, rp, ci, va, xv, yv, 1, nullptr), "CSR SpMV");
