@@ -32,6 +32,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "csr_spmv_gflops"
 UNIT = "GFLOP/s"
+# DRAM bytes of one csr_stream_kernel<double> launch on the 256^3 stencil, from the committed ncu capture
+# (5.751718 GB read + 115.587 MB written) - 1.0007x the algorithmic 5,863,223,204 bytes.
+NCU_TRAFFIC_BYTES = 5751718000 + 115587072
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -305,7 +308,9 @@ def run_single(args):
                    "rows": N, "nnz": nnz, "kernel": kname, "lanes": lanes, "cache": "inputs (5.9 GB) larger than L2 (126 MB)",
                    "step_ms_min": round(min(per), 5), "step_ms_max": round(max(per), 5)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "traffic": NCU_TRAFFIC_BYTES if (n == 256 and kname == "stream") else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one csr_stream_kernel launch "
+                                       "(profiles/r01_ncu_stream_final.txt); not measurable live", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": bytes_alg, "frac_of_8TBs_spec": round(achieved / 8000.0, 4)},
         "e2e": {"value": round(e2e_gflops, 2), "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
                 "ms_per_step": round(e2e_ms, 4), "call": "thsp_csr_plan_spmv_host_f64 (pinned x in, y out)"},
