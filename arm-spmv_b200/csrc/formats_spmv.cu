@@ -2,6 +2,8 @@
 //
 // Replaces ELLMatrixMatVector (src/mat_vec.cpp:97-121), COOMatirxMatVector (:18-42),
 // CSCMatrixMatVector (:69-95) and DIAMatrixMatVector (:123-146).  All HBM-bound.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -113,15 +115,9 @@ __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict
     const int e1 = (int)min((int64_t)nnz, e0 + kCooRun);
     int open_row = -1;
     double open_sum = 0.0;
-    for (int g = (int)e0; g < e1; g += 32) {
-        const int e = g + lane;
-        const bool ok = e < e1;
-        int r = -2;
-        double p = 0.0;
-        if (ok) {
-            r = ld_stream(row + e);
-            p = mul_rn(ld_stream(val + e), ld_gather(x + ld_stream(col + e)));
-        }
+
+    // One 32-entry step: segmented scan, chain with the open segment, emit closed segments.
+    auto step = [&](int g, int r, double p) {
         const int rl = __shfl_up_sync(full, r, 1);
         const bool head = (lane == 0) || (rl != r);
         const unsigned heads = __ballot_sync(full, head);
@@ -141,9 +137,29 @@ __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict
         }
         const int rn = __shfl_down_sync(full, r, 1);
         const int last = min(31, e1 - g - 1);
-        if (ok && lane != last && rn != r) atomicAdd(y + r, p);
+        if (g + lane < e1 && lane != last && rn != r) atomicAdd(y + r, p);
         open_row = __shfl_sync(full, r, last);
         open_sum = __shfl_sync(full, p, last);
+    };
+
+    // Four steps' worth of loads are issued before the first scan: 2 KB in flight per warp.
+    constexpr int U = 4;
+    for (int g = (int)e0; g < e1; g += 32 * U) {
+        int rr[U], cc[U];
+        double vv[U], xx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g + u * 32 + lane;
+            const bool ok = e < e1;
+            rr[u] = ok ? ld_stream(row + e) : -2;
+            cc[u] = ok ? ld_stream(col + e) : 0;
+            vv[u] = ok ? ld_stream(val + e) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xx[u] = (g + u * 32 + lane < e1) ? ld_gather(x + cc[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (g + u * 32 < e1) step(g + u * 32, rr[u], mul_rn(vv[u], xx[u]));
     }
     if (lane == 0 && open_row >= 0) atomicAdd(y + open_row, open_sum);
 }
@@ -230,6 +246,94 @@ __global__ void __launch_bounds__(kDiaRows) dia_kernel(int row_begin, int nrows,
     y[i] = acc;
 }
 
+// DIA, B200 path: the values of 32 consecutive rows are one contiguous run of 32*ndiags doubles,
+// so the CSR stream kernel's recipe applies with no index stream at all (8 B per entry instead
+// of 12): persistent CTAs, a warp per 32-row tile handed out round-robin, one TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) per tile into a per-warp shared-memory stage guarded by an
+// mbarrier, then each lane walks its row's diagonals in ascending d accumulating from y with
+// unfused mul/add - the reference's order and `j < nrow` guard, bit-identical.
+// A warp keeps two stages: the next tile is in flight while the current one is consumed.
+static constexpr int kDiaMaxOff = 64;   // offsets cached in shared memory; wider matrices use dia_kernel
+
+__global__ void __launch_bounds__(768, 1)
+    dia_stream_kernel(int row_begin, int nrows, int nrow_total, int ndiags, const int* __restrict__ off,
+                      const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, int stage_elems,
+                      int S)
+{
+    extern __shared__ __align__(128) unsigned char dia_smem[];
+    __shared__ int s_off[kDiaMaxOff];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    double* stage0 = reinterpret_cast<double*>(dia_smem) + (size_t)warp * S * stage_elems;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(dia_smem) + (size_t)W * S * stage_elems) + warp * 2;
+    if (threadIdx.x < ndiags) s_off[threadIdx.x] = off[threadIdx.x];
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int num_tiles = (nrows + 31) >> 5;
+    const int GW = gridDim.x * W;
+    const int gw = blockIdx.x * W + warp;
+    const uint64_t pol = policy_evict_first();
+    const size_t total = (size_t)nrows * ndiags;
+
+    auto issue = [&](int tile, int st) {
+        // elements [e0, e1) of `values`; e0 is a multiple of 32*ndiags -> 16 B aligned; the bulk copy
+        // takes the even part, a trailing odd element is fetched with an ordinary load
+        const size_t e0 = (size_t)tile * 32 * ndiags;
+        const size_t e1 = min(total, e0 + (size_t)32 * ndiags);
+        const unsigned n = (unsigned)(e1 - e0);
+        const unsigned nb = n & ~1u;
+        double* dst = stage0 + (size_t)st * stage_elems;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar + st, nb * 8u);
+            if (nb) bulk_g2s(dst, values + e0, nb * 8u, bar + st, pol);
+            if (n & 1u) dst[n - 1] = values[e1 - 1];
+        }
+    };
+
+    int st = 0;
+    unsigned par = 0u;   // bit s = phase parity of stage s
+    if (S == 2 && gw < num_tiles) issue(gw, 0);
+    for (int tile = gw; tile < num_tiles; tile += GW) {
+        const int next = tile + GW;
+        if (S == 2) {
+            if (next < num_tiles) issue(next, st ^ 1);   // next tile in flight while this one is consumed
+        } else {
+            issue(tile, 0);
+        }
+        const int i = tile * 32 + lane;             // row inside the block
+        double acc = i < nrows ? y[i] : 0.0;
+        mbar_wait(bar + st, (par >> st) & 1u);
+        par ^= 1u << st;
+        __syncwarp();
+        if (i < nrows) {
+            const double* sv = stage0 + (size_t)st * stage_elems + (size_t)lane * ndiags;
+            const int gi = row_begin + i;
+            constexpr int U = 9;
+            for (int d = 0; d < ndiags; d += U) {
+                double xx[U], vv[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = (d + u < ndiags) ? gi + s_off[d + u] : -1;
+                    ok[u] = (d + u < ndiags) && j >= 0 && j < nrow_total;
+                    xx[u] = ok[u] ? ld_gather(x + j) : 0.0;
+                    vv[u] = ok[u] ? sv[d + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u]) acc = add_rn(acc, mul_rn(vv[u], xx[u]));
+            }
+            y[i] = acc;
+        }
+        __syncwarp();
+        if (S == 2) st ^= 1;
+    }
+}
+
 }  // namespace thsp
 
 using namespace thsp;
@@ -287,6 +391,30 @@ int thsp_dia_spmv_rows_f64(int row_begin, int row_count, int nrow, int ndiags, c
 {
     if (ensure_device()) return 1;
     if (row_count <= 0 || ndiags <= 0) return 0;
+    // B200 path: TMA-fed stream kernel when a 32-row tile is small enough for two stages per warp.
+    if (ndiags <= kDiaMaxOff && ((((uintptr_t)values) & 15) == 0) && row_count >= 4096) {
+        const int stage_elems = (32 * ndiags + 1) & ~1;
+        static const int env_stages = getenv("THSP_DIA_STAGES") ? atoi(getenv("THSP_DIA_STAGES")) : 0;
+        const int S = env_stages == 1 || env_stages == 2 ? env_stages : 1;   // like CSR: warps in flight beat ring depth
+        const size_t per_warp = (size_t)S * stage_elems * sizeof(double) + 2 * sizeof(uint64_t);
+        int warps = (int)std::min<size_t>(24, (216 * 1024) / per_warp);
+        if (warps >= 4) {
+            const size_t smem = per_warp * warps;
+            static bool configured[16] = {};
+            int dev = 0;
+            THSP_CUDA(cudaGetDevice(&dev));
+            if (!configured[dev & 15]) {
+                THSP_CUDA(cudaFuncSetAttribute(dia_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                configured[dev & 15] = true;
+            }
+            const int tiles = div_up(row_count, 32);
+            const int grid = std::max(1, std::min(sm_count(), div_up(tiles, warps)));
+            dia_stream_kernel<<<grid, warps * 32, smem, as_stream(stream)>>>(row_begin, row_count, nrow, ndiags, offsets, values, x, y,
+                                                                           stage_elems, S);
+            THSP_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const size_t words = (size_t)kDiaRows * ndiags;
     const size_t smem = (words + words / 32 + 1) * sizeof(double);
     const int staged = smem <= 48 * 1024 ? 1 : 0;

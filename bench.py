@@ -277,6 +277,25 @@ def run_single(args):
                         "achieved_gbs": round(ell_bytes / (ell_ms * 1e-3) / 1e9, 1),
                         "frac": round(ell_bytes / (ell_ms * 1e-3) / 1e9 / peak, 4)}
         del E, ye
+        # DIA: no index stream at all (8 B per entry) - the format with the highest roofline on a stencil
+        Bc = H.CSRMatrix(nrow=N, ncol=N, row_ptr=A.row_ptr, col_ind=A.col_ind, values=A.values)
+        Dm = H.DIAMatrix(Bc)
+        yd2 = H.Vector(N)
+        yd2.Fill(0.0)
+        for _ in range(3):
+            H.DIAMatrixMatVector(Dm, x, yd2)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            H.DIAMatrixMatVector(Dm, x, yd2)
+        b.record()
+        torch.cuda.synchronize()
+        dia_ms = a.elapsed_time(b) / args.steps
+        dia_bytes = N * Dm.ndiags * 8 + Dm.ndiags * 4 + N * 8 + 2 * N * 8
+        extra["dia"] = {"ms_per_step": round(dia_ms, 4), "gflops": round(2.0 * nnz / (dia_ms * 1e-3) / 1e9, 2), "ndiags": Dm.ndiags,
+                        "achieved_gbs": round(dia_bytes / (dia_ms * 1e-3) / 1e9, 1), "frac": round(dia_bytes / (dia_ms * 1e-3) / 1e9 / peak, 4)}
+        del Dm, yd2, Bc
 
     # ---- the iterated loop (power iteration) on one GPU: the denominator of the multi-GPU runs
     if args.iterated_grid:
