@@ -8,14 +8,16 @@
 #include "matrix.h"
 #include "vector.h"
 
-// "<n>" then one "%20.16g" value per line (src/data_io.cpp:10-40)
-void VectorRead(const char* filename, Vector& x);
-void VectorWrite(const char* filename, const Vector& x);
+// Matrix Market "coordinate real general" file -> COO (file indices are 1-based, ours 0-based).
+// Prints the reference's progress lines and "### ROW=.., COL=.., NNZ=.."; exits on a bad file.
+void COOMatrixRead(const char* path, COOMatrix& A);
+// Read as COO, then convert on the GPU.
+void CSRMatrixRead(const char* path, CSRMatrix& A);
+void CSCMatrixRead(const char* path, CSCMatrix& A);
+void ELLMatrixRead(const char* path, ELLMatrix& A);
 
-// Matrix Market coordinate file -> COO (1-based -> 0-based); CSR/CSC/ELL = read COO + convert.
-void COOMatrixRead(const char* filename, COOMatrix& A);
-void CSRMatrixRead(const char* filename, CSRMatrix& A);
-void CSCMatrixRead(const char* filename, CSCMatrix& A);
-void ELLMatrixRead(const char* filename, ELLMatrix& A);
+// Plain text vectors: "<n>" then one "%20.16g" value per line (src/data_io.cpp:10-40).
+void VectorWrite(const char* path, const Vector& x);
+void VectorRead(const char* path, Vector& x);
 
 #endif  // DATA_IO_H

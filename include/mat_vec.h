@@ -9,30 +9,32 @@
 #include "matrix.h"
 #include "vector.h"
 
-// "Matirx" is the reference's spelling and part of its link interface.
-void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y);
-void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y);
-void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y);
+// ---- one GPU --------------------------------------------------------------------------------
+void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y);   // TMA-stream / vector / merge kernel, chosen per matrix
 void ELLMatrixMatVector(const ELLMatrix& A, const Vector& x, Vector& y);
 void DIAMatrixMatVector(const DIAMatrix& A, const Vector& x, Vector& y);
+void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y);
+void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y);   // "Matirx": the reference's spelling, part of its link interface
 
-// Partitioned variants.  The reference splits rows (columns for CSC) into `nthreads` equal
-// blocks placed on NUMA nodes, runs 50 repeats and prints "### <FMT> NUMA GFLOPS = ...".
-// Here the blocks are placed on min(nthreads, #GPUs) B200s with x replicated; the same line
-// is printed.  Unlike the reference (which drops the result for four of the five formats,
-// SURVEY.md A.3) the accumulated blocks are written back into y.
-void COOMatrixMatVectorNuma(const COOMatrix& A, const Vector& x, Vector& y, int nthreads);
+// ---- partitioned --------------------------------------------------------------------------
+// The reference splits rows (columns for CSC) into `nthreads` equal blocks placed on NUMA nodes,
+// runs 50 repeats and prints "### <FMT> NUMA GFLOPS = ...".  Here the blocks are placed on
+// min(nthreads, #GPUs) B200s with x replicated; the same line is printed.  Unlike the reference
+// (which drops the result for four of the five formats) the accumulated blocks
+// are written back into y.
 void CSRMatrixMatVectorNuma(const CSRMatrix& A, const Vector& x, Vector& y, int nthreads);
-void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int nthreads);
 void ELLMatrixMatVectorNuma(const ELLMatrix& A, const Vector& x, Vector& y, int nthreads);
 void DIAMatrixMatVectorNuma(const DIAMatrix& A, const Vector& x, Vector& y, int nthreads);
+void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int nthreads);
+void COOMatrixMatVectorNuma(const COOMatrix& A, const Vector& x, Vector& y, int nthreads);
 
-// pthread bodies of the reference's partitioned variants; `args` is a NumaNode4* (numa_node.h)
-// whose arrays are device pointers here.  Each runs one y_block += A_block * x on its GPU.
-void* COOMatrixMatVectorNumaThread(void* args);
-void* CSRMatrixMatVectorNumaThread(void* args);
-void* CSCMatrixMatVectorNumaThread(void* args);
-void* ELLMatrixMatVectorNumaThread(void* args);
-void* DIAMatrixMatVectorNumaThread(void* args);
+// Bodies of the reference's pthreads; `block` points at a NumaNode4CSR / ...ELL / ...DIA / ...CSC /
+// ...COO (numa_node.h) whose arrays are device pointers here.  Each runs one
+// y_block += A_block * x on the block's GPU and returns NULL.
+void* CSRMatrixMatVectorNumaThread(void* block);
+void* ELLMatrixMatVectorNumaThread(void* block);
+void* DIAMatrixMatVectorNumaThread(void* block);
+void* CSCMatrixMatVectorNumaThread(void* block);
+void* COOMatrixMatVectorNumaThread(void* block);
 
 #endif  // MAT_VEC_H

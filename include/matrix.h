@@ -1,8 +1,8 @@
 // matrix.h -- sparse matrix containers of the arm-spmv API, backed by the B200 library.
 //
-// Source-compatible with the reference's include/matrix.h:7-138: every public field, every
-// constructor / method signature is kept, so main.cpp and other callers recompile unchanged.
-// What changed underneath:
+// Source-compatible with the reference's include/matrix.h:7-138: every public field (name, type,
+// order) and every constructor / method signature is kept, so main.cpp and other callers
+// recompile unchanged.  What changed underneath:
 //   * arrays allocated by the library (converting constructors, copies, COOMatrixRead) live in
 //     CUDA managed memory: host code may still index them, kernels stream them from HBM;
 //   * pointer-taking constructors adopt caller memory exactly like the reference
@@ -18,137 +18,114 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-// Coordinate triples, any order, duplicates allowed.
+// ---------------------------------------------------------------------------------------------
+// COO: coordinate triples in any order, duplicates allowed (they add up in a product).
 class COOMatrix {
 public:
-    int nrow;
-    int ncol;
-    int nnz;
+    int nrow, ncol, nnz;              // shape and number of stored triples
+    int *row_ind, *col_ind;           // [nnz] each, 0-based
+    double* values;                   // [nnz]
 
-    int*    row_ind;
-    int*    col_ind;
-    double* values;
-
-    COOMatrix();
-    COOMatrix(int n, int m, int nnz, int* row_ind, int* col_ind, double* values);
-    COOMatrix(const COOMatrix& A);
     ~COOMatrix();
-    COOMatrix& operator=(const COOMatrix& A);
-
+    COOMatrix();
+    COOMatrix(const COOMatrix& other);                                                   // deep copy
+    COOMatrix(int rows, int cols, int entries, int* rows_of, int* cols_of, double* vals);  // adopts the arrays
+    COOMatrix& operator=(const COOMatrix& other);
     void Free();
 };
 
-// Compressed rows.  `diagonal` holds the row==col values packed in COO order (first nrow at most).
+// ---------------------------------------------------------------------------------------------
+// CSR: entries of row i are [row_ptr[i], row_ptr[i+1]).  `diagonal` holds the row==col values
+// packed in COO order (at most nrow of them) - the reference keeps it "for SymGS".
 class CSRMatrix {
 public:
-    int nrow;
-    int ncol;
+    int nrow, ncol;
+    int *row_ptr, *col_ind;           // [nrow+1], [nnz]
+    double *values, *diagonal;        // [nnz], [nrow]
 
-    int*    row_ptr;
-    int*    col_ind;
-    double* values;
-    double* diagonal;
-
-    CSRMatrix();
-    CSRMatrix(int n, int m, int* row_ptr, int* col_ind, double* values, double* diagonal);
-    CSRMatrix(const CSRMatrix& A);
-    CSRMatrix(const COOMatrix& A);   // stable by row: entries keep their COO order inside a row
     ~CSRMatrix();
-    CSRMatrix& operator=(const CSRMatrix& A);
-    CSRMatrix& operator=(const COOMatrix& A);
-
+    CSRMatrix();
+    CSRMatrix(const COOMatrix& coo);  // stable by row: inside a row entries keep their COO order
+    CSRMatrix(const CSRMatrix& other);
+    CSRMatrix(int rows, int cols, int* ptr, int* cols_of, double* vals, double* diag);    // adopts the arrays
+    CSRMatrix& operator=(const COOMatrix& coo);
+    CSRMatrix& operator=(const CSRMatrix& other);
     void Free();
 };
 
-// Compressed columns.
+// ---------------------------------------------------------------------------------------------
+// CSC: entries of column j are [col_ptr[j], col_ptr[j+1]).
 class CSCMatrix {
 public:
-    int nrow;
-    int ncol;
+    int nrow, ncol;
+    int *row_ind, *col_ptr;           // [nnz], [ncol+1]
+    double* values;                   // [nnz]
 
-    int*    row_ind;
-    int*    col_ptr;
-    double* values;
-
-    CSCMatrix();
-    CSCMatrix(int n, int m, int* row_ind, int* col_ptr, double* values);
-    CSCMatrix(const CSCMatrix& A);
-    CSCMatrix(const COOMatrix& A);
     ~CSCMatrix();
-    CSCMatrix& operator=(const CSCMatrix& A);
-    CSCMatrix& operator=(const COOMatrix& A);
-
+    CSCMatrix();
+    CSCMatrix(const COOMatrix& coo);  // stable by column
+    CSCMatrix(const CSCMatrix& other);
+    CSCMatrix(int rows, int cols, int* rows_of, int* ptr, double* vals);                  // adopts the arrays
+    CSCMatrix& operator=(const COOMatrix& coo);
+    CSCMatrix& operator=(const CSCMatrix& other);
     void Free();
 };
 
+// ---------------------------------------------------------------------------------------------
 // ELLPACK, COLUMN-major slab: slot k of row i is element [i + k*nrow]; padding is (col 0, 0.0).
 class ELLMatrix {
 public:
-    int nrow;
-    int ncol;
-    int nnz;
-    int nonzeros_in_row;
+    int nrow, ncol, nnz;
+    int nonzeros_in_row;              // slab width = longest row
+    int* col_ind;                     // [nrow * nonzeros_in_row]
+    double *values, *diagonal;        // [nrow * nonzeros_in_row], [nrow]
 
-    int*    col_ind;
-    double* values;
-    double* diagonal;
-
-    ELLMatrix();
-    ELLMatrix(int n, int m, int nnz, int nonzeros_in_row, int* col_ind, double* values, double* diagonal);
-    ELLMatrix(const ELLMatrix& A);
-    ELLMatrix(const COOMatrix& A);
     ~ELLMatrix();
-    ELLMatrix& operator=(const ELLMatrix& A);
-    ELLMatrix& operator=(const COOMatrix& A);
-
+    ELLMatrix();
+    ELLMatrix(const COOMatrix& coo);
+    ELLMatrix(const ELLMatrix& other);
+    ELLMatrix(int rows, int cols, int entries, int width, int* cols_of, double* vals, double* diag);   // adopts the arrays
+    ELLMatrix& operator=(const COOMatrix& coo);
+    ELLMatrix& operator=(const ELLMatrix& other);
     void Free();
 };
 
+// ---------------------------------------------------------------------------------------------
 // Declared by the reference (include/matrix.h:95-115) but only partly defined there
 // (src/matrix.cpp:619-632: no copy constructor, destructor, assignment or Free), so nothing can
 // use it.  Kept declaration-compatible; the three members the reference defines exist here too.
 class BlockMatrix {
 public:
-    int nrow;
-    int ncol;
-    int nnz;
-    int nblocks;
-
-    int*     block_size;
-    int*     row_ind;
-    int*     col_ind;
+    int nrow, ncol, nnz, nblocks;
+    int *block_size, *row_ind, *col_ind;
     double** values;
 
-    BlockMatrix();
-    BlockMatrix(int n, int m, int nnz, int nblocks, int* block_size, int* row_ind, int* col_ind, double** values);
-    BlockMatrix(const BlockMatrix& A);
-    BlockMatrix(const COOMatrix& A);
     ~BlockMatrix();
-    BlockMatrix& operator=(const BlockMatrix& A);
-    BlockMatrix& operator=(const COOMatrix& A);
-
+    BlockMatrix();
+    BlockMatrix(const COOMatrix& coo);
+    BlockMatrix(const BlockMatrix& other);
+    BlockMatrix(int rows, int cols, int entries, int blocks, int* sizes, int* rows_of, int* cols_of, double** vals);
+    BlockMatrix& operator=(const COOMatrix& coo);
+    BlockMatrix& operator=(const BlockMatrix& other);
     void Free();
 };
 
-// Diagonals, ROW-major: values[i*ndiags + d] is the entry of row i on diagonal offsets[d].
+// ---------------------------------------------------------------------------------------------
+// DIA, ROW-major: values[i*ndiags + d] is the entry of row i on diagonal offsets[d] (ascending).
 class DIAMatrix {
 public:
-    int nnz;
-    int nrow;
-    int ncol;
-    int ndiags;
+    int nnz, nrow, ncol;
+    int ndiags;                       // number of occupied diagonals
+    int* offsets;                     // [ndiags], column minus row
+    double* values;                   // [nrow * ndiags]
 
-    int*    offsets;
-    double* values;
-
-    DIAMatrix();
-    DIAMatrix(int n, int m, int ndiags, int* offsets, double* values);
-    DIAMatrix(const DIAMatrix& A);
-    DIAMatrix(const CSRMatrix& A);
     ~DIAMatrix();
-    DIAMatrix& operator=(const DIAMatrix& A);
-    DIAMatrix& operator=(const CSRMatrix& A);
-
+    DIAMatrix();
+    DIAMatrix(const CSRMatrix& csr);  // a duplicate (i,j) overwrites the earlier one
+    DIAMatrix(const DIAMatrix& other);
+    DIAMatrix(int rows, int cols, int diagonals, int* offs, double* vals);                // adopts the arrays
+    DIAMatrix& operator=(const CSRMatrix& csr);
+    DIAMatrix& operator=(const DIAMatrix& other);
     void Free();
 };
 

@@ -1,78 +1,56 @@
 // numa_node.h -- per-block descriptors of the partitioned SpMV (reference include/numa_node.h).
 //
-// Field-compatible with the reference.  In the reference `alloc` is a NUMA node and the arrays
-// sit in numa_alloc_onnode memory; here `alloc` is a CUDA device ordinal and the arrays are
-// cudaMalloc'ed on that device.  Row pointers of a block are rebased to start at 0
-// (src/mat_vec.cpp:260-263), which is also what keeps them int32 when the whole matrix has
-// more than 2^31 entries.
+// Field-compatible with the reference (same names and types).  There `alloc` is a NUMA node and
+// the arrays sit in numa_alloc_onnode memory; here `alloc` is a CUDA device ordinal and the
+// arrays are cudaMalloc'ed on that device.  Row pointers of a block are rebased to start at 0
+// (src/mat_vec.cpp:260-263), which is also what keeps them int32 when the whole matrix has more
+// than 2^31 entries.
 #ifndef NUMA_NODE_H
 #define NUMA_NODE_H
 
+// A run of COO entries.  Row indices stay global; the kernel subtracts start_row.
 class NumaNode4COO {
 public:
-    int     alloc;          // device holding this block
-    int     core_ind;       // block index
-    int     nnz;
-    int     start_row;
-    int     rows_per_node;
-    int*    sub_row_ind;
-    int*    sub_col_ind;
-    double* sub_values;
-    double* X;
-    double* Y;
+    int alloc, core_ind;                         // device holding the block, block index
+    int nnz, start_row, rows_per_node;
+    int *sub_row_ind, *sub_col_ind;              // [nnz] each, on device `alloc`
+    double *sub_values, *X, *Y;                  // [nnz], replica of x, this block's y
 };
 
+// A block of consecutive rows.
 class NumaNode4CSR {
 public:
-    int     alloc;
-    int     nnz;
-    int     core_ind;
-    int     start_row;
-    int     rows_per_node;
-    int*    sub_row_ptr;    // rebased: sub_row_ptr[0] == 0
-    int*    sub_col_ind;
-    double* sub_values;
-    double* X;              // full-length replica of x
-    double* Y;              // this block's rows of y
+    int alloc, nnz, core_ind;
+    int start_row, rows_per_node;
+    int *sub_row_ptr, *sub_col_ind;              // [rows_per_node+1] with sub_row_ptr[0] == 0, [nnz]
+    double *sub_values, *X, *Y;                  // [nnz], full-length replica of x, rows of y owned by the block
 };
 
+// A block of consecutive columns; Y is a full-length private result to be reduced.
 class NumaNode4CSC {
 public:
-    int     alloc;
-    int     nnz;
-    int     core_ind;
-    int     start_col;
-    int     cols_per_node;
-    int*    sub_col_ptr;    // rebased
-    int*    sub_row_ind;
-    double* sub_values;
-    double* X;              // this block's columns of x
-    double* Y;              // full-length private y
+    int alloc, nnz, core_ind;
+    int start_col, cols_per_node;
+    int *sub_col_ptr, *sub_row_ind;              // rebased column pointers, global row indices
+    double *sub_values, *X, *Y;                  // [nnz], the block's columns of x, full-length y
 };
 
+// A block of consecutive rows of the column-major slab: element [i + k*rows_per_node].
 class NumaNode4ELL {
 public:
-    int     alloc;
-    int     core_ind;
-    int     rows_per_node;
-    int     nonzeros_in_row;
-    int*    sub_col_ind;    // column-major slab of the block: [i + k*rows_per_node]
-    double* sub_values;
-    double* X;
-    double* Y;
+    int alloc, core_ind;
+    int rows_per_node, nonzeros_in_row;
+    int* sub_col_ind;
+    double *sub_values, *X, *Y;
 };
 
+// A block of consecutive rows of the row-major diagonals.
 struct NumaNode4DIA {
 public:
-    int     alloc;
-    int     core_ind;
-    int     start_row;
-    int     rows_per_node;
-    int     ndiags;
-    int*    offsets;
-    double* values;
-    double* X;
-    double* Y;
+    int alloc, core_ind;
+    int start_row, rows_per_node, ndiags;
+    int* offsets;
+    double *values, *X, *Y;
 };
 
 #endif  // NUMA_NODE_H

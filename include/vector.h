@@ -15,26 +15,28 @@
 
 class Vector {
 public:
-    int     size;
-    double* values;
+    int size;            // number of entries
+    double* values;      // [size]
 
-    Vector();
-    Vector(int n, double* values);   // adopts `values` (reference: src/vector.cpp:12)
-    Vector(const Vector& x);         // deep copy
     ~Vector();
+    Vector();
+    Vector(const Vector& other);              // deep copy
+    Vector(int length, double* storage);      // adopts `storage` (reference: src/vector.cpp:12)
 
-    Vector& operator=(double a);
-    Vector& operator=(const Vector& x);
+    Vector& operator=(const Vector& other);   // resize + copy
+    Vector& operator=(double a);              // same as Fill(a)
 
+    void Resize(int length);                  // contents are not preserved (src/vector.cpp:51-57)
     void Free();
-    void Resize(int n);              // contents are not preserved (src/vector.cpp:51-57)
-    void Fill(double a) const;
-    void FillRandom() const;         // host glibc rand()/RAND_MAX sequence, as in the reference
-    void Copy(const Vector& x) const;
-    void Scale(double a) const;
-    void Shift(double a) const;
-    void AddScaled(double a, const Vector& x) const;
-    void Add2Scaled(double a, const Vector& x, double b, const Vector& y) const;
+
+    // elementwise, on the GPU; `const` as in the reference although they write through `values`
+    void Fill(double a) const;                                                          // v = a
+    void Copy(const Vector& x) const;                                                   // v = x
+    void Scale(double a) const;                                                         // v *= a
+    void Shift(double a) const;                                                         // v += a
+    void AddScaled(double a, const Vector& x) const;                                    // v += a x
+    void Add2Scaled(double a, const Vector& x, double b, const Vector& y) const;        // v += a x + b y
+    void FillRandom() const;                  // host glibc rand()/RAND_MAX sequence, as in the reference
 };
 
 // true iff sizes match and every |x_i - y_i| <= 1e-6 (src/vector.cpp:161-171)
