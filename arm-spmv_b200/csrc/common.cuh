@@ -108,9 +108,54 @@ __device__ __forceinline__ float4 ld_stream4(const float* p)
                  : "l"(p));
     return v;
 }
+// Streaming loads with an L2 evict-first policy (createpolicy): a stream that is read once must
+// not push the gathered vector out of L2.
+__device__ __forceinline__ double ld_stream_ef(const double* p, uint64_t pol)
+{
+    double v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_ef(const float* p, uint64_t pol)
+{
+    float v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_ef(const int* p, uint64_t pol)
+{
+    int v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream4_ef(const int* p, uint64_t pol)
+{
+    int4 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream4_ef(const float* p, uint64_t pol)
+{
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream2_ef(const double* p, uint64_t pol)
+{
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
 // x gathers: read-only path, allocate in L1 (neighbouring rows hit the same lines).
 template <typename T>
 __device__ __forceinline__ T ld_gather(const T* p) { return __ldg(p); }
+// Random gathers with no reuse inside an SM: do not allocate in L1.
+__device__ __forceinline__ double ld_gather_na(const double* p) { return ld_stream(p); }
+__device__ __forceinline__ float ld_gather_na(const float* p) { return ld_stream(p); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v)

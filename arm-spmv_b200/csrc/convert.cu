@@ -7,14 +7,16 @@
 // The reference's "histogram, running sum, backward fill with pre-decrement" is a STABLE
 // counting sort of the entries by row (column for CSC): inside a bucket entries keep their COO
 // order and duplicates survive.  On the GPU:
-//   1. one pass over the keys builds the bucket histogram (one atomic per run of equal
-//      adjacent keys) and notes whether the keys are already non-decreasing;
-//   2. a three-phase exclusive scan of the histogram is row_ptr / col_ptr;
-//   3. already sorted  -> the permutation is the identity (stencil generators, sorted .mtx);
-//      otherwise       -> stable LSD radix sort of (key, original index), 8 bits per pass,
-//                         ceil(log2(nbuckets)/8) passes, ranks inside a CTA from
-//                         __match_any_sync so equal digits keep their order;
-//   4. one gather writes the payload (ELL: slot = position - row_ptr[row], column-major).
+//   1. one pass over the keys notes whether they are already non-decreasing;
+//   2. already sorted  -> the entries are copied through (stencil generators, sorted .mtx);
+//      otherwise       -> stable LSD radix sort of the whole entries (key, other index, value),
+//                         8 bits per pass, ceil(log2(nbuckets)/8) passes, ranks inside a CTA from
+//                         warp match masks so equal digits keep their order; the last pass writes
+//                         straight into the output arrays;
+//      then the bucket pointers are read off the sorted keys (ptr[r] = first position whose key
+//      is >= r) without atomics;
+//   3. ELL: a thread per row writes its slots (and its padding) column-major from the row-sorted
+//      entries.
 // The packed `diagonal` (row==col entries in COO order) is a stable stream compaction.
 // Everything here is integer/byte work bound by HBM traffic.
 #include <algorithm>
@@ -155,50 +157,84 @@ __global__ void __launch_bounds__(256) hist_kernel(int n, const int* __restrict_
 }
 
 // ================================================================== LSD radix sort ========
-// One pass = digit histogram per CTA tile -> exclusive scan over (digit-major, tile-minor) counts
-// -> stable scatter.  A tile is 4096 consecutive elements; warp w owns elements
-// [w*512, (w+1)*512) of it and walks them in 16 rounds of 32 (coalesced loads).
-// Stable rank of an element = (elements with the same digit earlier in the tile): inside a warp
-// it comes from __match_any_sync against a warp-private running counter in shared memory (no CTA
-// barrier per round), across warps from one prefix over the eight warp counters per digit.
-// Elements are then placed in shared memory in sorted order and written out so that consecutive
-// threads write consecutive addresses of a digit run.
+// Stable LSD radix sort of whole entries (key, other index, value) held as three arrays, 8 bits per
+// pass.  One pass = digit histogram per CTA tile -> exclusive scan over (digit-major, tile-minor)
+// counts -> stable scatter.  The entries travel with their keys, so every pass reads and writes
+// whole cache lines and no random gather is left at the end (the earlier (key, index) sort spent
+// 40 % of its time gathering 12-byte payloads from random sectors: profiles/r01_conv_*).
+// A tile is 4096 consecutive entries; warp w owns entries [w*512, (w+1)*512) of it and walks them
+// in 16 rounds of 32 (coalesced loads).  Stable rank of an entry = (entries with the same digit
+// earlier in the tile): inside a warp it comes from a ballot-built match mask against a
+// warp-private running counter in shared memory (plain load/store by the first lane of each digit
+// group - no shared-memory atomics, which cost 2 cycles per lane), across warps from one prefix
+// over the eight warp counters per digit.  Entries are then placed in shared memory in sorted order and
+// written out so that consecutive threads write consecutive addresses of a digit run.
 static constexpr int kRadixThreads = 256;
 static constexpr int kRadixWarps = kRadixThreads / 32;
 static constexpr int kRadixRounds = 16;
-static constexpr int kRadixTile = kRadixThreads * kRadixRounds;  // 4096 keys per CTA
+static constexpr int kRadixTile = kRadixThreads * kRadixRounds;  // 4096 entries per CTA
+
+// Lanes of the warp whose 8-bit digit equals this lane's, from eight ballots.  __match_any_sync
+// (SASS MATCH.ANY) gives the same mask in one instruction but retires only one warp per ~60
+// cycles per SM on B200 - it alone made a histogram pass run at 0.6 TB/s (profiles/r01_conv_*).
+__device__ __forceinline__ unsigned match_digit(int d, bool ok)
+{
+    const unsigned full = 0xffffffffu;
+    unsigned m = __ballot_sync(full, ok);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1;
+        const unsigned bal = __ballot_sync(full, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return ok ? m : 0u;
+}
 
 __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(int n, const int* __restrict__ key, int shift,
                                                                    int* __restrict__ counts, int nblk)
 {
-    __shared__ int h[256];
+    __shared__ int wcnt[kRadixWarps][256];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    h[threadIdx.x] = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kRadixWarps; ++i) wcnt[i][threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kRadixTile;
-#pragma unroll 4
+    const int base = blockIdx.x * kRadixTile + w * (32 * kRadixRounds);
+    int kv[kRadixRounds];
+#pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
-        const int k = base + r * kRadixThreads + threadIdx.x;
-        const int d = k < n ? ((ld_stream(key + k) >> shift) & 255) : 256 + lane;
-        const unsigned peers = __match_any_sync(full, d);          // one atomic per distinct digit in the warp
-        if (k < n && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&h[d], __popc(peers));
+        const int k = base + r * 32 + lane;
+        kv[r] = k < n ? ld_stream(key + k) : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; ++r) {
+        const bool ok = kv[r] >= 0;
+        const int d = (kv[r] >> shift) & 255;
+        const unsigned peers = match_digit(d, ok);
+        if (ok && (peers & ((1u << lane) - 1u)) == 0) wcnt[w][d] += __popc(peers);   // one lane per distinct digit
+        __syncwarp();
     }
     __syncthreads();
-    counts[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+    int tot = 0;
+#pragma unroll
+    for (int i = 0; i < kRadixWarps; ++i) tot += wcnt[i][threadIdx.x];
+    counts[threadIdx.x * nblk + blockIdx.x] = tot;
 }
 
-// idx_in == nullptr means the identity (first pass).
 __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, const int* __restrict__ key_in,
-                                                                      const int* __restrict__ idx_in, int shift,
+                                                                      const int* __restrict__ oth_in,
+                                                                      const double* __restrict__ val_in, int shift,
                                                                       const int* __restrict__ offsets, int nblk,
-                                                                      int* __restrict__ key_out, int* __restrict__ idx_out)
+                                                                      int* __restrict__ key_out, int* __restrict__ oth_out,
+                                                                      double* __restrict__ val_out)
 {
+    extern __shared__ __align__(16) unsigned char radix_smem[];
+    double* s_val = reinterpret_cast<double*>(radix_smem);            // [kRadixTile]
+    int* s_key = reinterpret_cast<int*>(s_val + kRadixTile);          // [kRadixTile]
+    int* s_oth = s_key + kRadixTile;                                  // [kRadixTile]
     __shared__ int wcnt[kRadixWarps][256];   // per-warp digit counters, later exclusive warp offsets
     __shared__ int tile_off[256];            // first position of each digit inside the sorted tile
     __shared__ int gbase[256];               // where this tile's run of each digit starts in the output
-    __shared__ int s_key[kRadixTile];
-    __shared__ int s_idx[kRadixTile];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tile = blockIdx.x * kRadixTile;
@@ -208,20 +244,18 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
     gbase[threadIdx.x] = offsets[threadIdx.x * nblk + blockIdx.x];
     __syncthreads();
 
-    int kv[kRadixRounds], iv[kRadixRounds], rk[kRadixRounds];  // key, index, rank inside the warp's segment
+    int kv[kRadixRounds], rk[kRadixRounds];  // key, rank inside the warp's segment (later: position in the tile)
 #pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
         const int e = w * (32 * kRadixRounds) + r * 32 + lane;   // position inside the tile
-        const bool ok = e < tile_n;
-        kv[r] = ok ? key_in[tile + e] : 0;
-        iv[r] = ok ? (idx_in ? idx_in[tile + e] : tile + e) : 0;
+        kv[r] = e < tile_n ? ld_stream(key_in + tile + e) : 0;
     }
 #pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
         const int e = w * (32 * kRadixRounds) + r * 32 + lane;
         const bool ok = e < tile_n;
-        const int d = ok ? ((kv[r] >> shift) & 255) : 256 + lane;  // invalid lanes match nobody
-        const unsigned peers = __match_any_sync(full, d);
+        const int d = (kv[r] >> shift) & 255;
+        const unsigned peers = match_digit(d, ok);
         const int before = __popc(peers & ((1u << lane) - 1u));
         int base = 0;
         if (ok) base = wcnt[w][d];
@@ -245,14 +279,37 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
         tile_off[d] = excl;
     }
     __syncthreads();
+    // keys into their sorted slots; then the payload of each entry follows its key (loads issued
+    // only now: sixteen (index, value) pairs in flight per thread, no registers held across the ranking)
 #pragma unroll
     for (int r = 0; r < kRadixRounds; ++r) {
         const int e = w * (32 * kRadixRounds) + r * 32 + lane;
         if (e < tile_n) {
             const int d = (kv[r] >> shift) & 255;
-            const int pos = tile_off[d] + wcnt[w][d] + rk[r];
-            s_key[pos] = kv[r];
-            s_idx[pos] = iv[r];
+            rk[r] = tile_off[d] + wcnt[w][d] + rk[r];
+            s_key[rk[r]] = kv[r];
+        }
+    }
+    {
+        int ov[kRadixRounds];
+        double vv[kRadixRounds];
+#pragma unroll
+        for (int r = 0; r < kRadixRounds; ++r) {
+            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+            ov[r] = e < tile_n ? ld_stream(oth_in + tile + e) : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < kRadixRounds; ++r) {
+            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+            vv[r] = e < tile_n ? ld_stream(val_in + tile + e) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < kRadixRounds; ++r) {
+            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+            if (e < tile_n) {
+                s_oth[rk[r]] = ov[r];
+                s_val[rk[r]] = vv[r];
+            }
         }
     }
     __syncthreads();
@@ -260,65 +317,155 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
         const int k = s_key[t];
         const int d = (k >> shift) & 255;
         const int out = gbase[d] + (t - tile_off[d]);
-        key_out[out] = k;
-        idx_out[out] = s_idx[t];
+        if (key_out) key_out[out] = k;
+        oth_out[out] = s_oth[t];
+        val_out[out] = s_val[t];
     }
 }
 
-// Sort (key, index) stably by key in [0, nbuckets).  Returns device pointers to the sorted keys
-// and the permutation (scratch slots 6/7, valid until the next conversion call on this device).
-static int stable_sort_by_key(int n, int nbuckets, const int* key, const int** sorted_key, const int** perm, cudaStream_t s)
+static constexpr size_t kRadixSmem = (size_t)kRadixTile * (sizeof(double) + 2 * sizeof(int));   // 64 KB
+
+// Sort the entries (key, oth, val) stably by key in [0, nbuckets).  The last pass writes the other
+// index and the value to (oth_final, val_final) when given - else they stay in scratch - and the
+// sorted keys always to scratch.  *sorted_key / *sorted_oth / *sorted_val point at the result
+// (scratch slot 6, valid until the next conversion call on this device).
+static int stable_sort_entries(int n, int nbuckets, const int* key, const int* oth, const double* val, int* oth_final,
+                               double* val_final, const int** sorted_key, const int** sorted_oth, const double** sorted_val,
+                               cudaStream_t s)
 {
     int bits = 1;
     while (bits < 31 && (1 << bits) < nbuckets) ++bits;
     const int passes = (bits + 7) / 8;
     const int nblk = div_up(n, kRadixTile);
-    int* buf = static_cast<int*>(scratch(sizeof(int) * 4 * (size_t)n, 6));
+    // two ping-pong sets of (val, key, oth); a set's value array comes first so it stays 16 B aligned
+    const size_t np = ((size_t)n + 3) & ~(size_t)3;
+    const size_t set_bytes = np * (sizeof(double) + 2 * sizeof(int));
+    unsigned char* buf = static_cast<unsigned char*>(scratch(2 * set_bytes, 6));
     int* counts = static_cast<int*>(scratch(sizeof(int) * (256 * (size_t)nblk + 1), 7));
     if (!buf || !counts) return 1;
-    int* kbuf[2] = {buf, buf + (size_t)n};
-    int* ibuf[2] = {buf + 2 * (size_t)n, buf + 3 * (size_t)n};
+    static bool configured[16] = {};
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 15]) {
+        THSP_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRadixSmem));
+        configured[dev & 15] = true;
+    }
+    double* vbuf[2];
+    int *kbuf[2], *obuf[2];
+    for (int i = 0; i < 2; ++i) {
+        vbuf[i] = reinterpret_cast<double*>(buf + i * set_bytes);
+        kbuf[i] = reinterpret_cast<int*>(vbuf[i] + np);
+        obuf[i] = kbuf[i] + np;
+    }
     const int* kin = key;
-    const int* iin = nullptr;
+    const int* oin = oth;
+    const double* vin = val;
     for (int p = 0; p < passes; ++p) {
+        const bool last = p == passes - 1;
+        int* ko = kbuf[p & 1];
+        int* oo = (last && oth_final) ? oth_final : obuf[p & 1];
+        double* vo = (last && val_final) ? val_final : vbuf[p & 1];
         radix_hist_kernel<<<nblk, kRadixThreads, 0, s>>>(n, kin, 8 * p, counts, nblk);
         THSP_LAUNCH_CHECK();
         if (exclusive_scan(256 * nblk, counts, counts, s)) return 1;
-        radix_scatter_kernel<<<nblk, kRadixThreads, 0, s>>>(n, kin, iin, 8 * p, counts, nblk, kbuf[p & 1], ibuf[p & 1]);
+        radix_scatter_kernel<<<nblk, kRadixThreads, kRadixSmem, s>>>(n, kin, oin, vin, 8 * p, counts, nblk, ko, oo, vo);
         THSP_LAUNCH_CHECK();
-        kin = kbuf[p & 1];
-        iin = ibuf[p & 1];
+        kin = ko;
+        oin = oo;
+        vin = vo;
     }
     *sorted_key = kin;
-    *perm = iin;
+    *sorted_oth = oin;
+    *sorted_val = vin;
+    return 0;
+}
+
+// ================================================== bucket pointers from sorted keys ======
+__global__ void __launch_bounds__(256) sorted_check_kernel(int n, const int* __restrict__ key, int* __restrict__ unsorted)
+{
+    int bad = 0;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k + 1 < n; k += (int64_t)gridDim.x * 256)
+        if (ld_stream(key + k) > __ldg(key + k + 1)) bad = 1;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsorted, 1);
+}
+
+// ptr[r] = first position p with key[p] >= r, for r in [0, nbuckets], from NON-DECREASING keys:
+// thread p fills the buckets in (key[p-1], key[p]].  Gaps of 8 or more buckets (stretches of
+// empty rows) are queued in shared memory and filled by the whole CTA with coalesced stores; all
+// gaps together are nbuckets stores.  No atomics - the earlier atomic histogram serialised on
+// hub rows (3.7 ms on the R-MAT matrix).
+__global__ void __launch_bounds__(256) boundaries_kernel(int n, int nbuckets, const int* __restrict__ key, int* __restrict__ ptr)
+{
+    __shared__ int q_lo[256], q_hi[256], q_pos[256];
+    __shared__ int q_n;
+    if (threadIdx.x == 0) q_n = 0;
+    __syncthreads();
+    const int64_t p64 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p64 <= n) {
+        const int p = (int)p64;
+        const int prev = p == 0 ? -1 : ld_stream(key + p - 1);
+        const int cur = p == n ? nbuckets : ld_stream(key + p);
+        const int lo = max(prev + 1, 0), hi = min(cur, nbuckets);   // fill ptr[lo..hi]
+        if (hi - lo >= 8) {
+            const int q = atomicAdd(&q_n, 1);
+            q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = p;
+        } else {
+            for (int r = lo; r <= hi; ++r) ptr[r] = p;
+        }
+    }
+    __syncthreads();
+    const int nq = q_n;
+    for (int q = 0; q < nq; ++q)
+        for (int r = q_lo[q] + threadIdx.x; r <= q_hi[q]; r += 256) ptr[r] = q_pos[q];
+}
+
+static int keys_unsorted(int n, const int* key, int* unsorted_host, cudaStream_t s)
+{
+    int* flag = static_cast<int*>(scratch(sizeof(int), 1));
+    if (!flag) return 1;
+    THSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    sorted_check_kernel<<<std::min(div_up(n, 256), sm_count() * 32), 256, 0, s>>>(n, key, flag);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaMemcpyAsync(unsorted_host, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int bucket_pointers(int nbuckets, int n, const int* sorted_key, int* ptr, cudaStream_t s)
+{
+    boundaries_kernel<<<div_up((int64_t)n + 1, 256), 256, 0, s>>>(n, nbuckets, sorted_key, ptr);
+    THSP_LAUNCH_CHECK();
     return 0;
 }
 
 // =============================================================== payload placement ========
-// perm == nullptr: identity.
-__global__ void __launch_bounds__(256) gather_kernel(int n, const int* __restrict__ perm, const int* __restrict__ other,
-                                                     const double* __restrict__ val, int* __restrict__ out_other,
-                                                     double* __restrict__ out_val)
+__global__ void __launch_bounds__(256) copy_entries_kernel(int n, const int* __restrict__ oth, const double* __restrict__ val,
+                                                           int* __restrict__ out_oth, double* __restrict__ out_val)
 {
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p >= n) return;
-    const int k = perm ? perm[p] : p;
-    out_other[p] = other[k];
-    out_val[p] = val[k];
+    out_oth[p] = ld_stream(oth + p);
+    out_val[p] = ld_stream(val + p);
 }
 
-__global__ void __launch_bounds__(256) ell_place_kernel(int n, int nrow, const int* __restrict__ sorted_row,
-                                                        const int* __restrict__ perm, const int* __restrict__ row_ptr,
+// ELL slab from row-sorted entries: a thread owns a row and writes its slots in ascending order,
+// padding included (column 0, +0.0: src/matrix.cpp:476-483) - consecutive threads store
+// consecutive addresses of one slot column, and the slab needs no separate zero fill.
+__global__ void __launch_bounds__(256) ell_write_kernel(int nrow, int width, const int* __restrict__ ptr,
                                                         const int* __restrict__ col, const double* __restrict__ val,
                                                         int* __restrict__ out_col, double* __restrict__ out_val)
 {
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= n) return;
-    const int k = perm ? perm[p] : p;
-    const int r = sorted_row[p];
-    const size_t at = (size_t)(p - row_ptr[r]) * nrow + r;
-    out_col[at] = col[k];
-    out_val[at] = val[k];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= nrow) return;
+    const int s = ptr[r], len = ptr[r + 1] - s;
+#pragma unroll 4
+    for (int k = 0; k < width; ++k) {
+        const bool in = k < len;
+        const int c = in ? __ldg(col + s + k) : 0;
+        const double v = in ? __ldg(val + s + k) : 0.0;
+        out_col[(size_t)k * nrow + r] = c;
+        out_val[(size_t)k * nrow + r] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256) max_len_kernel(int nrow, const int* __restrict__ cnt, int* __restrict__ out)
@@ -390,26 +537,26 @@ static int pack_diagonal(int nnz, const int* ri, const int* ci, const double* va
     return 0;
 }
 
-// Common front half of COO->CSR/CSC/ELL: ptr = exclusive scan of the key histogram, plus the
-// stable order.  *sorted_key/*perm are nullptr-permutation (identity) when already sorted.
-static int bucket_order(int nbuckets, int nnz, const int* key, int* ptr, const int** sorted_key, const int** perm,
-                        cudaStream_t s)
+// COO -> (ptr, other index, value) ordered stably by key: the shared body of COO->CSR and COO->CSC.
+static int coo_to_compressed(int nbuckets, int nnz, const int* key, const int* oth, const double* val, int* ptr, int* out_oth,
+                             double* out_val, cudaStream_t s)
 {
-    THSP_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int) * ((size_t)nbuckets + 1), s));
-    *sorted_key = key;
-    *perm = nullptr;
-    if (nnz <= 0) return 0;
-    int* flag = static_cast<int*>(scratch(sizeof(int), 1));
-    if (!flag) return 1;
-    THSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-    hist_kernel<<<std::min(div_up(nnz, 256), sm_count() * 16), 256, 0, s>>>(nnz, key, ptr, flag);
-    THSP_LAUNCH_CHECK();
-    if (exclusive_scan(nbuckets, ptr, ptr, s)) return 1;
+    if (nnz <= 0) {
+        THSP_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int) * ((size_t)nbuckets + 1), s));
+        return 0;
+    }
     int unsorted = 0;
-    THSP_CUDA(cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    THSP_CUDA(cudaStreamSynchronize(s));
-    if (unsorted) return stable_sort_by_key(nnz, nbuckets, key, sorted_key, perm, s);
-    return 0;
+    if (keys_unsorted(nnz, key, &unsorted, s)) return 1;
+    if (!unsorted) {   // stencil generators, sorted .mtx files: the stable order is the identity
+        if (bucket_pointers(nbuckets, nnz, key, ptr, s)) return 1;
+        copy_entries_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, oth, val, out_oth, out_val);
+        THSP_LAUNCH_CHECK();
+        return 0;
+    }
+    const int *sk, *so;
+    const double* sv;
+    if (stable_sort_entries(nnz, nbuckets, key, oth, val, out_oth, out_val, &sk, &so, &sv, s)) return 1;
+    return bucket_pointers(nbuckets, nnz, sk, ptr, s);
 }
 
 // ============================================================================ DIA ==========
@@ -465,12 +612,7 @@ int thsp_coo2csr(int nrow, int ncol, int nnz, const int* row_ind, const int* col
     (void)ncol;
     if (ensure_device()) return 1;
     cudaStream_t s = as_stream(stream);
-    const int *sk, *perm;
-    if (bucket_order(nrow, nnz, row_ind, row_ptr, &sk, &perm, s)) return 1;
-    if (nnz > 0) {
-        gather_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, perm, col_ind, val, out_col_ind, out_val);
-        THSP_LAUNCH_CHECK();
-    }
+    if (coo_to_compressed(nrow, nnz, row_ind, col_ind, val, row_ptr, out_col_ind, out_val, s)) return 1;
     if (diagonal || ndiag) return pack_diagonal(nnz, row_ind, col_ind, val, nrow, diagonal, ndiag, s);
     return 0;
 }
@@ -480,14 +622,7 @@ int thsp_coo2csc(int nrow, int ncol, int nnz, const int* row_ind, const int* col
 {
     (void)nrow;
     if (ensure_device()) return 1;
-    cudaStream_t s = as_stream(stream);
-    const int *sk, *perm;
-    if (bucket_order(ncol, nnz, col_ind, col_ptr, &sk, &perm, s)) return 1;
-    if (nnz > 0) {
-        gather_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, perm, row_ind, val, out_row_ind, out_val);
-        THSP_LAUNCH_CHECK();
-    }
-    return 0;
+    return coo_to_compressed(ncol, nnz, col_ind, row_ind, val, col_ptr, out_row_ind, out_val, as_stream(stream));
 }
 
 int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_stream_t stream)
@@ -516,17 +651,21 @@ int thsp_coo2ell(int nrow, int ncol, int nnz, const int* row_ind, const int* col
     (void)ncol;
     if (ensure_device()) return 1;
     cudaStream_t s = as_stream(stream);
-    const size_t total = (size_t)nrow * (size_t)width;
-    if (total) {
-        THSP_CUDA(cudaMemsetAsync(out_col_ind, 0, sizeof(int) * total, s));   // padding: column 0
-        THSP_CUDA(cudaMemsetAsync(out_val, 0, sizeof(double) * total, s));    // padding: +0.0
-    }
-    int* rp = static_cast<int*>(scratch(sizeof(int) * ((size_t)nrow + 2), 2));
-    if (!rp) return 1;
-    const int *sk, *perm;
-    if (bucket_order(nrow, nnz, row_ind, rp, &sk, &perm, s)) return 1;
-    if (nnz > 0) {
-        ell_place_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, nrow, sk, perm, rp, col_ind, val, out_col_ind, out_val);
+    if (nrow > 0 && width > 0) {
+        int* rp = static_cast<int*>(scratch(sizeof(int) * ((size_t)nrow + 2), 2));
+        if (!rp) return 1;
+        const int* sc = col_ind;
+        const double* sv = val;
+        if (nnz <= 0) {
+            THSP_CUDA(cudaMemsetAsync(rp, 0, sizeof(int) * ((size_t)nrow + 1), s));
+        } else {
+            int unsorted = 0;
+            if (keys_unsorted(nnz, row_ind, &unsorted, s)) return 1;
+            const int* sk = row_ind;
+            if (unsorted && stable_sort_entries(nnz, nrow, row_ind, col_ind, val, nullptr, nullptr, &sk, &sc, &sv, s)) return 1;
+            if (bucket_pointers(nrow, nnz, sk, rp, s)) return 1;
+        }
+        ell_write_kernel<<<div_up(nrow, 256), 256, 0, s>>>(nrow, width, rp, sc, sv, out_col_ind, out_val);
         THSP_LAUNCH_CHECK();
     }
     if (diagonal || ndiag) return pack_diagonal(nnz, row_ind, col_ind, val, nrow, diagonal, ndiag, s);

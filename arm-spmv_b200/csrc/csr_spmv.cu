@@ -23,6 +23,8 @@
 //          completed through a carry array and a fix-up pass.  For power-law rows.
 //
 // The plan picks kernel and L from the row-length histogram (thsp_csr_plan_create).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -304,111 +306,355 @@ static StreamCfg default_stream_cfg(int nrow, int nnz)
 }
 
 // ========================================================================= MERGE ==========
-// nnz-balanced: run t = entries [t*kMergeRun, (t+1)*kMergeRun) belongs to one warp whatever
-// the row boundaries are.
-//   1. binary search: row_lo = the row holding the run's first entry;
-//   2. every later row that STARTS inside the run scatters its id to mark[start - e0] in shared
-//      memory (atomicMax, so that of several empty rows starting at one entry the last - the
-//      non-empty one - wins); a running max over the marks gives each entry's row;
-//   3. 32 entries at a time: products, segmented inclusive scan (segments = equal rows), the
-//      segment still open at the end of a group is chained into the next group;
-//   4. a row that ends inside the run is added into y by the lane holding its last entry -
-//      unless it began in an earlier run, in which case its partial goes to carry slot 2t;
+// Merge-path CSR (Merrill & Garland): the list of row ends (row_ptr[1..nrow]) and the list of entry
+// indices (0..nnz-1) are merged conceptually; every warp gets one RUN of kMergeRun consecutive
+// steps of that merge, whatever the row lengths are - a run holds at most kMergeRun entries and
+// at most kMergeRun row ends, so neither a hub row nor a stretch of empty rows unbalances it.
+//   0. merge_partition_kernel: the (row, entry) coordinate where each run starts (binary search
+//      along the run's diagonal).  Part of the plan; the stateless entry point recomputes it.
+//   1. the run's col_ind / val are read with coalesced streaming loads (L2 evict-first, so that
+//      the stream does not push x out of L2), kMergeU gathers of x in flight per lane, and the
+//      products are parked in shared memory in a lane-blocked, padded layout;
+//   2. every row that STARTS inside the run scatters its id to mark[start - j0] (atomicMax, so of
+//      several empty rows starting at one entry the last - the non-empty one - wins);
+//   3. lane l then owns kMergeIPT CONSECUTIVE entries: it adds them left to right, closing a row
+//      at every mark.  Rows that lie inside one lane are added into y directly.  The piece before
+//      a lane's first mark (head) and after its last (tail) belong to rows that cross lanes: one
+//      segmented warp scan over the tails gives every lane the sum carried in from the lanes to
+//      its left; the lane that holds the row's end adds carry + head into y;
+//   4. the row in which the run STARTED, if it began in an earlier run, goes to carry slot 2t;
 //      whatever is still open when the run ends goes to carry slot 2t+1.
 // The fix-up pass adds the carry partials of each row in slot (= entry) order.  Rows written
-// directly and rows completed by the fix-up are disjoint, so there are no atomics on y and the
-// result is deterministic.
-// Summation order: inside a group a Hillis-Steele tree; groups of one row are chained left to
-// right (open + group); run partials are added left to right by the fix-up.
-static constexpr int kMergeRun = 1024;  // entries per warp-run
+// directly and rows completed by the fix-up are disjoint: no atomics on y, deterministic.
+// Summation order: left to right inside a lane's kMergeIPT entries; lanes combined by a
+// Hillis-Steele segmented scan; run partials added left to right by the fix-up.
+static constexpr int kMergeIPT = 16;                      // entries owned by a lane
+static constexpr int kMergeRun = 32 * kMergeIPT;          // merge steps per warp-run
+static constexpr int kMergeWarps = 4;                     // warps per CTA (independent of each other)
+static constexpr int kMergePad = kMergeRun + kMergeRun / kMergeIPT;   // lane stride kMergeIPT+1: conflict-free
+static constexpr int kMergeU = 8;                         // x gathers in flight per lane
 
-template <typename V>
-__global__ void __launch_bounds__(256) csr_merge_kernel(int nrow, int nnz, const int* __restrict__ row_ptr,
-                                                        const int* __restrict__ col, const V* __restrict__ val,
-                                                        const V* __restrict__ x, V* __restrict__ y,
-                                                        int* __restrict__ carry_row, V* __restrict__ carry_val, int nruns)
+__device__ __forceinline__ int merge_slot(int q) { return q + q / kMergeIPT; }
+
+__global__ void __launch_bounds__(256) merge_partition_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, int nruns,
+                                                              int run_len, int* __restrict__ part_row, int* __restrict__ part_ent)
 {
-    __shared__ int mark_all[8][kMergeRun];
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t > nruns) return;
+    const int64_t total = (int64_t)nrow + nnz;
+    const int64_t d = min((int64_t)t * run_len, total);
+    // smallest i with row_ptr[i+1] > d - i - 1: rows < i have ended, entries < d - i are consumed
+    int lo = (int)max((int64_t)0, d - nnz), hi = (int)min(d, (int64_t)nrow);
+    while (lo < hi) {
+        const int mid = (int)(((int64_t)lo + hi) >> 1);
+        if ((int64_t)__ldg(row_ptr + mid + 1) <= d - mid - 1) lo = mid + 1; else hi = mid;
+    }
+    part_row[t] = lo;
+    part_ent[t] = (int)(d - lo);
+}
+
+template <typename V, bool kNoAlloc>
+__global__ void __launch_bounds__(kMergeWarps * 32, 8)
+    csr_merge_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ col, const V* __restrict__ val,
+                     const V* __restrict__ x, V* __restrict__ y, const int* __restrict__ part_row,
+                     const int* __restrict__ part_ent, int* __restrict__ carry_row, V* __restrict__ carry_val, int nruns)
+{
+    __shared__ V s_prod_all[kMergeWarps][kMergePad];
+    __shared__ int s_mark_all[kMergeWarps][kMergePad];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int run = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int run = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
     if (run >= nruns) return;  // warp-uniform; no CTA-wide barriers below
-    int* mark = mark_all[threadIdx.x >> 5];
-    const int e0 = run * kMergeRun;
-    const int e1 = min(e0 + kMergeRun, nnz);
+    V* s_prod = s_prod_all[threadIdx.x >> 5];
+    int* s_mark = s_mark_all[threadIdx.x >> 5];
+    const int i0 = __ldg(part_row + run), i1 = __ldg(part_row + run + 1);
+    const int j0 = __ldg(part_ent + run), j1 = __ldg(part_ent + run + 1);
+    const int n = j1 - j0;  // entries of this run, <= kMergeRun
+    const uint64_t pol = policy_evict_first();
+    const int* colp = col + j0;
+    const V* valp = val + j0;
 
-    int lo = 0, hi = nrow;  // row_ptr[lo] <= e0 < row_ptr[hi]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(row_ptr + mid) <= e0) lo = mid; else hi = mid;
+    // ---- 1+2. stream the run, gather x, park the products; meanwhile mark the row starts -----
+    int cc[kMergeU];
+#pragma unroll
+    for (int u = 0; u < kMergeU; ++u) {
+        const int q = u * 32 + lane;
+        cc[u] = q < n ? ld_stream_ef(colp + q, pol) : 0;
     }
-    const int row_lo = lo;
-    const bool first_shared = __ldg(row_ptr + row_lo) < e0;
-
-    for (int i = lane; i < kMergeRun; i += 32) mark[i] = -1;
-    if (lane == 0) carry_row[2 * run] = -1;
+    for (int q = lane; q < kMergePad; q += 32) s_mark[q] = -1;
     __syncwarp();
-    for (int rb = row_lo + 1;; rb += 32) {
+    for (int rb = i0 + 1; rb <= i1; rb += 32) {
         const int r = rb + lane;
-        const int s = (r <= nrow) ? __ldg(row_ptr + r) : 0x7fffffff;
-        if (r < nrow && s < e1) atomicMax(&mark[s - e0], r);
-        if (__any_sync(full, s >= e1)) break;
+        if (r <= i1) {
+            const int s = __ldg(row_ptr + r);      // >= j0 by construction of the partition
+            if (s < j1) atomicMax(&s_mark[merge_slot(s - j0)], r);
+        }
     }
-    __syncwarp();
-
-    auto emit = [&](int r, V p) {
-        if (r == row_lo && first_shared) {
-            carry_row[2 * run] = r;
-            carry_val[2 * run] = p;
-        } else {
-            y[r] = add_rn(y[r], p);
-        }
-    };
-
-    int run_row = row_lo;
-    int open_row = -1;
-    V open_sum = V(0);
-    for (int g = e0; g < e1; g += 32) {
-        const int e = g + lane;
-        const bool ok = e < e1;
-        V p = V(0);
-        if (ok) p = mul_rn(ld_stream(val + e), ld_gather(x + ld_stream(col + e)));
-        int m = ok ? mark[e - e0] : -1;
-        if (lane == 0) m = max(m, run_row);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(full, m, d);
-            if (lane >= d) m = max(m, t);
-        }
-        run_row = __shfl_sync(full, m, 31);
-        const int r = ok ? m : -2;
-        const int rl = __shfl_up_sync(full, r, 1);
-        const bool head = (lane == 0) || (rl != r);
-        const unsigned heads = __ballot_sync(full, head);
-        const int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+    for (int k = 0; k < kMergeIPT; k += kMergeU) {
+        V xx[kMergeU], vv[kMergeU];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const V q = __shfl_up_sync(full, p, d);
-            if (lane - d >= seg_start) p = add_rn(p, q);
-        }
-        const int r0 = __shfl_sync(full, r, 0);
-        if (open_row >= 0) {
-            if (r0 == open_row) {
-                if (seg_start == 0) p = add_rn(open_sum, p);
-            } else if (lane == 0) {
-                emit(open_row, open_sum);  // that row ended exactly at the group boundary
+        for (int u = 0; u < kMergeU; ++u) xx[u] = ((k + u) * 32 + lane < n) ? (kNoAlloc ? ld_gather_na(x + cc[u]) : ld_gather(x + cc[u])) : V(0);
+#pragma unroll
+        for (int u = 0; u < kMergeU; ++u) vv[u] = ((k + u) * 32 + lane < n) ? ld_stream_ef(valp + (k + u) * 32 + lane, pol) : V(0);
+        if (k + kMergeU < kMergeIPT) {
+#pragma unroll
+            for (int u = 0; u < kMergeU; ++u) {
+                const int q = (k + kMergeU + u) * 32 + lane;
+                cc[u] = q < n ? ld_stream_ef(colp + q, pol) : 0;
             }
         }
-        const int rn = __shfl_down_sync(full, r, 1);
-        const int last = min(31, e1 - g - 1);
-        if (ok && lane != last && rn != r) emit(r, p);
-        open_row = __shfl_sync(full, r, last);
-        open_sum = __shfl_sync(full, p, last);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kMergeU; ++u) s_prod[merge_slot((k + u) * 32 + lane)] = mul_rn(vv[u], xx[u]);
     }
-    if (lane == 0) {
-        carry_row[2 * run + 1] = open_row;
-        carry_val[2 * run + 1] = open_sum;
+    __syncwarp();
+
+    // ---- 3. lane-blocked reduction ------------------------------------------------------
+    const int base = lane * kMergeIPT;
+    const int cnt = max(0, min(kMergeIPT, n - base));
+    const int sb = lane * (kMergeIPT + 1);
+    int mk[kMergeIPT];
+    int lm = -1;
+#pragma unroll
+    for (int k = 0; k < kMergeIPT; ++k) {
+        mk[k] = k < cnt ? s_mark[sb + k] : -1;
+        lm = max(lm, mk[k]);
+    }
+    // row of the lane's first entry: i0 or the last mark in the lanes to its left
+    int inc_row = lm;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(full, inc_row, d);
+        if (lane >= d) inc_row = max(inc_row, t);
+    }
+    int row_in = __shfl_up_sync(full, inc_row, 1);
+    row_in = lane == 0 ? i0 : max(i0, row_in);
+    const int open_row = max(i0, __shfl_sync(full, inc_row, 31));
+
+    int cur = row_in;
+    V sum = V(0), head = V(0);
+    bool has_mark = false, head_any = false, any = false;
+#pragma unroll
+    for (int k = 0; k < kMergeIPT; ++k) {
+        if (k < cnt) {
+            if (mk[k] >= 0) {
+                if (!has_mark) {
+                    head = sum;
+                    head_any = any;
+                    has_mark = true;
+                } else {
+                    y[cur] = add_rn(y[cur], sum);   // a row that starts and ends inside this lane
+                }
+                cur = mk[k];
+                sum = V(0);
+            }
+            sum = any || has_mark ? add_rn(sum, s_prod[sb + k]) : s_prod[sb + k];
+            any = true;
+        }
+    }
+    // segmented scan over the lanes' tails; a lane with a mark starts a new segment
+    V tail = sum;
+    bool flag = has_mark;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const V tv = __shfl_up_sync(full, tail, d);
+        const bool tf = __shfl_up_sync(full, (int)flag, d) != 0;
+        if (lane >= d) {
+            if (!flag) tail = add_rn(tv, tail);
+            flag = flag || tf;
+        }
+    }
+    const V carry_in = __shfl_up_sync(full, tail, 1);   // inclusive scan of lane-1 = what flows into this lane
+    const bool first_shared = __ldg(row_ptr + i0) < j0;
+    if (lane == 0) carry_row[2 * run] = -1;
+    __syncwarp();
+    if (has_mark && (lane > 0 || head_any)) {
+        V tot = head;
+        if (lane > 0) tot = head_any ? add_rn(carry_in, head) : carry_in;
+        if (row_in == i0 && first_shared) {
+            carry_row[2 * run] = i0;
+            carry_val[2 * run] = tot;
+        } else {
+            y[row_in] = add_rn(y[row_in], tot);
+        }
+    }
+    if (lane == 31) {
+        carry_row[2 * run + 1] = n > 0 ? open_row : -1;
+        carry_val[2 * run + 1] = tail;
+    }
+}
+
+// ---- register-blocked variant ---------------------------------------------------------------
+// Same algorithm, but a lane fetches ITS 16 consecutive entries itself (four 128-bit col_ind loads,
+// eight 128-bit val loads) instead of going through a coalesced load + shared-memory transpose:
+// the products never touch shared memory, which is left to L1 - on B200 the unified L1/shared
+// array also holds the lines of outstanding gather misses, and a kernel that fills it with staging
+// buffers starves its own gathers (measured: profiles/r01_merge_*).  Lane blocks are aligned to
+// absolute multiples of 16 entries, so a run of 496 merge steps, widened to whole blocks, still
+// fits 32 lanes; entries of a block outside the run are masked.
+static constexpr int kMbIPT = 16;
+static constexpr int kMbRun = 31 * kMbIPT;
+static constexpr int kMbPad = 32 * (kMbIPT + 1);
+
+template <bool kVec>
+__device__ __forceinline__ void mb_load8(const int* p, int limit, int (&c)[8], uint64_t pol)
+{
+    // limit = entries readable from p
+    if (kVec && limit >= 8) {
+        const int4 a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = k < limit ? ld_stream_ef(p + k, pol) : 0;
+    }
+}
+template <bool kVec>
+__device__ __forceinline__ void mb_load8(const double* p, int limit, double (&v)[8], uint64_t pol)
+{
+    if (kVec && limit >= 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const double2 a = ld_stream2_ef(p + k, pol);
+            v[k] = a.x; v[k + 1] = a.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.0;
+    }
+}
+template <bool kVec>
+__device__ __forceinline__ void mb_load8(const float* p, int limit, float (&v)[8], uint64_t pol)
+{
+    if (kVec && limit >= 8) {
+        const float4 a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.f;
+    }
+}
+
+template <typename V, bool kVec, bool kNoAlloc>
+__global__ void __launch_bounds__(kMergeWarps * 32, 8)
+    csr_merge_blocked_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                             const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y,
+                             const int* __restrict__ part_row, const int* __restrict__ part_ent, int* __restrict__ carry_row,
+                             V* __restrict__ carry_val, int nruns)
+{
+    __shared__ int s_mark_all[kMergeWarps][kMbPad];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int run = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
+    if (run >= nruns) return;  // warp-uniform; no CTA-wide barriers below
+    int* s_mark = s_mark_all[threadIdx.x >> 5];
+    const int i0 = __ldg(part_row + run), i1 = __ldg(part_row + run + 1);
+    const int j0 = __ldg(part_ent + run), j1 = __ldg(part_ent + run + 1);
+    const int n = j1 - j0;                       // entries of this run, <= kMbRun
+    const int blk0 = j0 & ~(kMbIPT - 1);         // the run widened to whole 16-entry blocks starts here
+    const int eb = blk0 + lane * kMbIPT;         // first entry of this lane's block
+    const int ks = max(j0 - eb, 0), ke = min(j1 - eb, kMbIPT);   // the lane's entries of the run: k in [ks, ke)
+    const bool mine = ks < ke;
+    const int sb = lane * (kMbIPT + 1);
+
+    // the lane's first eight column indices are requested before anything else
+    const uint64_t pol = policy_evict_first();   // the streams are read once: keep L2 for x
+    int cc[8];
+    if (mine) mb_load8<kVec>(col + eb, nnz - eb, cc, pol);
+    // ---- row starts inside the run -> marks ---------------------------------------------
+    for (int q = lane; q < kMbPad; q += 32) s_mark[q] = -1;
+    __syncwarp();
+    for (int rb = i0 + 1; rb <= i1; rb += 32) {
+        const int r = rb + lane;
+        if (r <= i1) {
+            const int s = __ldg(row_ptr + r);      // >= j0 by construction of the partition
+            if (s < j1) {
+                const int q = s - blk0;
+                atomicMax(&s_mark[q + q / kMbIPT], r);
+            }
+        }
+    }
+    __syncwarp();
+    int lm = -1;
+#pragma unroll
+    for (int k = 0; k < kMbIPT; ++k)
+        if (k >= ks && k < ke) lm = max(lm, s_mark[sb + k]);
+    // row of the lane's first entry: i0 or the last mark in the lanes to its left
+    int inc_row = lm;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(full, inc_row, d);
+        if (lane >= d) inc_row = max(inc_row, t);
+    }
+    int row_in = __shfl_up_sync(full, inc_row, 1);
+    row_in = lane == 0 ? i0 : max(i0, row_in);
+    const int open_row = max(i0, __shfl_sync(full, inc_row, 31));
+
+    // ---- the lane's entries, left to right ------------------------------------------------
+    int cur = row_in;
+    V sum = V(0), head = V(0);
+    bool has_mark = false, head_any = false, any = false;
+#pragma unroll
+    for (int h = 0; h < kMbIPT; h += 8) {
+        V xx[8], vv[8];
+        if (mine) {
+            if (h > 0) mb_load8<kVec>(col + eb + h, nnz - eb - h, cc, pol);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = h + k >= ks && h + k < ke;
+                xx[k] = ok ? (kNoAlloc ? ld_gather_na(x + cc[k]) : ld_gather(x + cc[k])) : V(0);
+            }
+            mb_load8<kVec>(val + eb + h, nnz - eb - h, vv, pol);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (h + k >= ks && h + k < ke) {
+                    const int m = s_mark[sb + h + k];
+                    if (m >= 0) {
+                        if (!has_mark) {
+                            head = sum;
+                            head_any = any;
+                            has_mark = true;
+                        } else {
+                            y[cur] = add_rn(y[cur], sum);   // a row that starts and ends inside this lane
+                        }
+                        cur = m;
+                        sum = V(0);
+                    }
+                    const V p = mul_rn(vv[k], xx[k]);
+                    sum = (any || has_mark) ? add_rn(sum, p) : p;
+                    any = true;
+                }
+            }
+        }
+    }
+    // segmented scan over the lanes' tails; a lane with a mark starts a new segment
+    V tail = sum;
+    bool flag = has_mark;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const V tv = __shfl_up_sync(full, tail, d);
+        const bool tf = __shfl_up_sync(full, (int)flag, d) != 0;
+        if (lane >= d) {
+            if (!flag) tail = add_rn(tv, tail);
+            flag = flag || tf;
+        }
+    }
+    const V carry_in = __shfl_up_sync(full, tail, 1);   // inclusive scan of lane-1 = what flows into this lane
+    const bool first_shared = __ldg(row_ptr + i0) < j0;
+    if (lane == 0) carry_row[2 * run] = -1;
+    __syncwarp();
+    if (has_mark && (lane > 0 || head_any)) {
+        V tot = head;
+        if (lane > 0) tot = head_any ? add_rn(carry_in, head) : carry_in;
+        if (row_in == i0 && first_shared) {
+            carry_row[2 * run] = i0;
+            carry_val[2 * run] = tot;
+        } else {
+            y[row_in] = add_rn(y[row_in], tot);
+        }
+    }
+    if (lane == 31) {
+        carry_row[2 * run + 1] = n > 0 ? open_row : -1;
+        carry_val[2 * run + 1] = tail;
     }
 }
 
@@ -442,20 +688,62 @@ __global__ void zero_kernel(int64_t n, V* __restrict__ y)
     if (i < n) y[i] = V(0);
 }
 
+// THSP_MERGE_VARIANT (tuning): 0 = register-blocked, L1-allocating gathers (default), 1 = same with
+// non-allocating gathers, 2 / 3 = shared-memory transpose with L1-allocating / non-allocating gathers.
+static int merge_variant()
+{
+    static const int v = getenv("THSP_MERGE_VARIANT") ? atoi(getenv("THSP_MERGE_VARIANT")) : 0;
+    return v;
+}
+static inline int merge_run_len() { return merge_variant() >= 2 ? kMergeRun : kMbRun; }
+static inline int merge_runs(int nrow, int nnz)
+{
+    const int len = merge_run_len();
+    return (int)(((int64_t)nrow + nnz + len - 1) / len);
+}
+
+// part = nruns+1 row coordinates followed by nruns+1 entry coordinates
+static int merge_partition(int nrow, int nnz, const int* rp, int* part, cudaStream_t s)
+{
+    const int nruns = merge_runs(nrow, nnz);
+    merge_partition_kernel<<<div_up(nruns + 1, 256), 256, 0, s>>>(nrow, nnz, rp, nruns, merge_run_len(), part, part + nruns + 1);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename V>
 static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* val, const V* x, V* y, int acc,
-                     cudaStream_t s)
+                     const int* part, cudaStream_t s)
 {
     if (!acc && nrow > 0) {
         zero_kernel<V><<<div_up(nrow, 256), 256, 0, s>>>(nrow, y);
         THSP_LAUNCH_CHECK();
     }
     if (nnz <= 0 || nrow <= 0) return 0;
-    const int nruns = div_up(nnz, kMergeRun);
+    const int nruns = merge_runs(nrow, nnz);
     int* crow = static_cast<int*>(scratch(sizeof(int) * 2 * (size_t)nruns, 2));
     V* cval = static_cast<V*>(scratch(sizeof(V) * 2 * (size_t)nruns, 3));
     if (!crow || !cval) return 1;
-    csr_merge_kernel<V><<<div_up(nruns, 8), 256, 0, s>>>(nrow, nnz, rp, col, val, x, y, crow, cval, nruns);
+    if (!part) {   // no plan: partition on the fly
+        int* p = static_cast<int*>(scratch(sizeof(int) * 2 * ((size_t)nruns + 1), 0));
+        if (!p || merge_partition(nrow, nnz, rp, p, s)) return 1;
+        part = p;
+    }
+    const int grid = div_up(nruns, kMergeWarps), block = kMergeWarps * 32;
+    const int* pr = part;
+    const int* pe = part + nruns + 1;
+    const bool vec = ((((uintptr_t)val) | ((uintptr_t)col)) & 15) == 0;   // 128-bit loads of whole lane blocks
+    switch (merge_variant()) {
+        case 2: csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
+        case 3: csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
+        case 1:
+            if (vec) csr_merge_blocked_kernel<V, true, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            else csr_merge_blocked_kernel<V, false, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            break;
+        default:
+            if (vec) csr_merge_blocked_kernel<V, true, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            else csr_merge_blocked_kernel<V, false, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+    }
     THSP_LAUNCH_CHECK();
     csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y);
     THSP_LAUNCH_CHECK();
@@ -524,6 +812,7 @@ struct HostPipe {
 
 struct thsp_csr_plan {
     HostPipe* pipe = nullptr;
+    int* merge_part = nullptr;   // merge-path run coordinates (device), built when the merge kernel is first used
     int nrow, ncol, nnz, value_bytes;
     const int* row_ptr;
     const int* col_ind;
@@ -548,7 +837,7 @@ static int dispatch(int kernel, int lanes, const StreamCfg* cfg, int nrow, int n
             StreamCfg c = cfg ? *cfg : default_stream_cfg<V>(nrow, nnz);
             return run_stream<V>(c, sm_count(), nrow, nnz, rp, col, val, x, y, acc, s);
         }
-        case THSP_CSR_MERGE: return run_merge<V>(nrow, nnz, rp, col, val, x, y, acc, s);
+        case THSP_CSR_MERGE: return run_merge<V>(nrow, nnz, rp, col, val, x, y, acc, nullptr, s);
     }
     set_error("unknown CSR kernel id %d", kernel);
     return 2;
@@ -579,6 +868,15 @@ template <typename V>
 static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s)
 {
     if (p->nrow <= 0) return 0;
+    if (p->kernel == THSP_CSR_MERGE) {
+        if (!p->merge_part && p->nnz > 0) {   // the run table belongs to the matrix: build it once
+            thsp_csr_plan* mp = const_cast<thsp_csr_plan*>(p);
+            const int nruns = merge_runs(p->nrow, p->nnz);
+            THSP_CUDA(cudaMalloc(&mp->merge_part, sizeof(int) * 2 * ((size_t)nruns + 1)));
+            if (merge_partition(p->nrow, p->nnz, p->row_ptr, mp->merge_part, s)) return 1;
+        }
+        return run_merge<V>(p->nrow, p->nnz, p->row_ptr, p->col_ind, static_cast<const V*>(p->val), x, y, acc, p->merge_part, s);
+    }
     if (p->kernel == THSP_CSR_STREAM)
         return run_stream<V>(p->stream_cfg, p->ctas, p->nrow, p->nnz, p->row_ptr, p->col_ind,
                              static_cast<const V*>(p->val), x, y, acc, s);
@@ -676,6 +974,7 @@ int thsp_csr_plan_destroy(thsp_csr_plan* plan)
         if (hp->s_out) cudaStreamDestroy(hp->s_out);
         delete hp;
     }
+    if (plan && plan->merge_part) cudaFree(plan->merge_part);
     delete plan;
     return 0;
 }
@@ -782,11 +1081,36 @@ int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, 
 static int build_host_pipe(thsp_csr_plan* p, cudaStream_t s)
 {
     HostPipe* hp = new HostPipe();
-    // ~1M rows per chunk, at most 32 chunks; a single chunk for small matrices or the merge kernel
-    int n = p->kernel == THSP_CSR_MERGE ? 1 : std::min(32, std::max(1, p->nrow / (1 << 20)));
+    // Row chunks: small at both ends, large in the middle.  The call cannot finish before the last
+    // piece of x has arrived + the last chunk is multiplied + its rows of y have left, and nothing
+    // leaves before the first piece of x is in: short first/last chunks shorten exactly those two
+    // exposed transfers, while few large chunks in between keep the per-chunk stream/event overhead
+    // down (measured on this box: 55 GB/s one way, 46 GB/s each way when both directions are busy).
+    // A single chunk for small matrices or the merge kernel.
+    std::vector<int> sizes;
+    if (p->kernel == THSP_CSR_MERGE || p->nrow < (1 << 21)) {
+        sizes.push_back(p->nrow);
+    } else {
+        static const int env_first = getenv("THSP_HOST_CHUNK0") ? atoi(getenv("THSP_HOST_CHUNK0")) : 0;
+        static const int env_cap = getenv("THSP_HOST_CHUNKMAX") ? atoi(getenv("THSP_HOST_CHUNKMAX")) : 0;
+        const int first = env_first > 0 ? env_first : (1 << 18), cap = env_cap > 0 ? env_cap : (1 << 22);
+        std::vector<int> ramp;
+        int64_t used = 0;
+        for (int sz = first; sz < cap && used + 2 * (int64_t)sz <= p->nrow / 2; sz *= 2) {
+            ramp.push_back(sz);
+            used += 2 * (int64_t)sz;
+        }
+        const int64_t mid = p->nrow - used;
+        const int nmid = (int)std::max<int64_t>(1, (mid + cap - 1) / cap);
+        for (int v : ramp) sizes.push_back(v);
+        for (int i = 0; i < nmid; ++i) sizes.push_back((int)(mid * (i + 1) / nmid / 32 * 32 - mid * i / nmid / 32 * 32));
+        for (size_t i = ramp.size(); i-- > 0;) sizes.push_back(ramp[i]);
+    }
+    const int n = (int)sizes.size();
     hp->nchunks = n;
     hp->row0.resize(n + 1);
-    for (int c = 0; c <= n; ++c) hp->row0[c] = (int)((int64_t)p->nrow * c / n / 32 * 32);
+    hp->row0[0] = 0;
+    for (int c = 0; c < n; ++c) hp->row0[c + 1] = std::min<int64_t>(p->nrow, (int64_t)hp->row0[c] + sizes[c]);
     hp->row0[n] = p->nrow;
     hp->cmin.assign(n, 0x7fffffff);
     hp->cmax.assign(n, -1);

@@ -1,0 +1,247 @@
+// exchange.cu -- the vector half of one power-iteration step fused with its exchange over NVLink.
+//
+// The reference has no iterated loop; composed from its own calls a step is
+//     y = A x ; s = vec_dot(y, y) ; x = vec_axpby(1/sqrt(s), y, 0, y)        (src/vec_vec.cpp:15-53)
+// Row-partitioned over the GPUs of one box (src/mat_vec.cpp:230-297 made multi-GPU) the dot needs the
+// partial sums of all ranks and the next SpMV needs the pieces of x that other ranks own.  Both
+// exchanges are a few bytes to a few MB: calling a collective library for them costs more in
+// launch + rendezvous latency than the transfer itself.  Here the kernels that PRODUCE the data
+// store it straight into the peers' memory (peer pointers into a symmetric allocation, NVLink),
+// followed by a release flag; the kernels that CONSUME it acquire the flag.  One stream, no host
+// round trip, no collective call in the loop:
+//
+//   thsp_xchg_sumsq_publish_f64   per-CTA partial sums of y^2 (fixed tree) -> the last CTA adds them
+//                                 in CTA order, stores the rank's partial into slot [parity][rank]
+//                                 of EVERY rank's control block, then the iteration number into
+//                                 the matching flag.
+//   thsp_xchg_scale_push_f64      waits until the flags of all ranks show this iteration, adds the
+//                                 partials in rank order (every rank gets the same bits),
+//                                 x_own = y / sqrt(sum) into the local replica and, for the index
+//                                 ranges other ranks read, into their replicas as well; when all
+//                                 CTAs are done the last one raises the "halo from <rank>" flag
+//                                 on those ranks.
+//   thsp_xchg_wait                one thread spins until the halo flags of the given source ranks
+//                                 show the iteration; launched in front of the rows that read
+//                                 remote parts of x.
+//
+// Control block (uint64 words, symmetric memory, zero-initialised): [0,32) partial sums as double
+// bits [parity][rank], [32,64) their flags, [64,80) halo flags [source rank], [80] timeout marker.
+// Two parities are enough: a rank can only be one publish ahead of the slowest reader, because
+// its next scale waits for that reader's next partial.  Spins give up after ~15 s and set word 80
+// instead of hanging the GPU.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace thsp {
+
+static constexpr int kXThreads = 256;
+static constexpr int kXMaxRanks = 16;
+static constexpr int kXPart = 0, kXPartFlag = 32, kXHalo = 64, kXErr = 80;
+static constexpr long long kXSpinLimit = 30000000000LL;   // cycles (~15 s)
+
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until(const uint64_t* flag, uint64_t want, uint64_t* err)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want) {
+        if (clock64() - t0 > kXSpinLimit) {
+            *err = 1;
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+__device__ __forceinline__ double block_sum_x(double v)
+{
+    __shared__ double ws[kXThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < kXThreads / 32 ? ws[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) r = add_rn(r, __shfl_xor_sync(0xffffffffu, r, o));
+    }
+    __syncthreads();
+    return r;   // valid in thread 0
+}
+
+struct XPeers {
+    uint64_t* ctrl[kXMaxRanks];
+};
+
+__global__ void __launch_bounds__(kXThreads) xchg_sumsq_publish_kernel(int64_t n, const double* __restrict__ y,
+                                                                       double* __restrict__ part, unsigned* __restrict__ ticket,
+                                                                       uint64_t iter, int world, int rank, XPeers peers)
+{
+    __shared__ bool last;
+    const int64_t stride = (int64_t)gridDim.x * kXThreads;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kXThreads + threadIdx.x; i < n; i += stride) {
+        const double v = y[i];
+        acc = add_rn(acc, mul_rn(v, v));
+    }
+    const double r = block_sum_x(acc);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = r;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double tot = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kXThreads) tot = add_rn(tot, part[i]);   // fixed order per thread
+    tot = block_sum_x(tot);
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        const int par = (int)(iter & 1);
+        for (int p = 0; p < world; ++p) st_relaxed_sys(peers.ctrl[p] + kXPart + par * kXMaxRanks + rank, (uint64_t)__double_as_longlong(tot));
+        __threadfence_system();
+        for (int p = 0; p < world; ++p) st_release_sys(peers.ctrl[p] + kXPartFlag + par * kXMaxRanks + rank, iter);
+    }
+}
+
+struct XDests {
+    double* x[kXMaxRanks];        // the destination rank's replica of x
+    uint64_t* ctrl[kXMaxRanks];   // its control block
+    int64_t lo[kXMaxRanks], hi[kXMaxRanks];   // global index range of x it reads from this rank
+    int n;
+};
+
+__global__ void __launch_bounds__(kXThreads) xchg_scale_push_kernel(int64_t n, const double* __restrict__ y, uint64_t* ctrl,
+                                                                    unsigned* __restrict__ ticket, uint64_t iter, int world, int rank,
+                                                                    double* __restrict__ x_local, int64_t offset, XDests dst,
+                                                                    double* __restrict__ sumsq_out)
+{
+    __shared__ double s_inv;
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        const int par = (int)(iter & 1);
+        double tot = 0.0;
+        for (int r = 0; r < world; ++r) {   // rank order: the same bits on every rank
+            spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
+            tot = add_rn(tot, __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r)));
+        }
+        s_inv = 1.0 / sqrt(tot);
+        if (blockIdx.x == 0 && sumsq_out) *sumsq_out = tot;
+    }
+    __syncthreads();
+    const double inv = s_inv;
+    const int64_t stride = (int64_t)gridDim.x * kXThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kXThreads + threadIdx.x; i < n; i += stride) {
+        const double v = mul_rn(inv, y[i]);   // vec_axpby's beta == 0 branch: w = alpha * x
+        const int64_t g = offset + i;
+        x_local[g] = v;
+        for (int d = 0; d < dst.n; ++d)
+            if (g >= dst.lo[d] && g < dst.hi[d]) dst.x[d][g] = v;
+    }
+    if (dst.n == 0) return;
+    __threadfence_system();   // this thread's remote stores are visible before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *ticket = 0;
+        __threadfence_system();
+        for (int d = 0; d < dst.n; ++d) st_release_sys(dst.ctrl[d] + kXHalo + rank, iter);
+    }
+}
+
+__global__ void xchg_wait_kernel(uint64_t* ctrl, uint64_t iter, unsigned src_mask)
+{
+    if (threadIdx.x != 0) return;
+    for (int r = 0; r < kXMaxRanks; ++r)
+        if (src_mask & (1u << r)) spin_until(ctrl + kXHalo + r, iter, ctrl + kXErr);
+}
+
+}  // namespace thsp
+
+using namespace thsp;
+
+extern "C" {
+
+int thsp_xchg_ctrl_bytes(void) { return 128 * (int)sizeof(uint64_t); }
+
+// work: 2 unsigned tickets (zero-initialised) followed by space for the per-CTA partial sums
+// (thsp_xchg_work_bytes()), private to this rank.
+int thsp_xchg_work_bytes(void) { return 64 + 8 * 4096; }
+
+int thsp_xchg_sumsq_publish_f64(int64_t n, const double* y, uint64_t iter, int world, int rank, void* const* peer_ctrl, void* work,
+                                thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    THSP_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "bad world / rank");
+    XPeers pe;
+    for (int p = 0; p < kXMaxRanks; ++p) pe.ctrl[p] = p < world ? static_cast<uint64_t*>(peer_ctrl[p]) : nullptr;
+    int grid = (int)std::min<int64_t>(4096, std::max<int64_t>(1, (n + kXThreads * 8 - 1) / (kXThreads * 8)));
+    grid = std::min(grid, sm_count() * 8);
+    unsigned* ticket = static_cast<unsigned*>(work);
+    double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
+    xchg_sumsq_publish_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(n, y, part, ticket, iter, world, rank, pe);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int world, int rank, void* ctrl_local, void* work,
+                             double* x_local, int64_t offset, int ndest, double* const* dest_x, void* const* dest_ctrl,
+                             const int64_t* dest_lo, const int64_t* dest_hi, double* sumsq_out, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    THSP_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "bad world / rank");
+    THSP_REQUIRE(ndest >= 0 && ndest < kXMaxRanks, "too many destinations");
+    XDests d;
+    d.n = ndest;
+    for (int k = 0; k < kXMaxRanks; ++k) {
+        d.x[k] = k < ndest ? dest_x[k] : nullptr;
+        d.ctrl[k] = k < ndest ? static_cast<uint64_t*>(dest_ctrl[k]) : nullptr;
+        d.lo[k] = k < ndest ? dest_lo[k] : 0;
+        d.hi[k] = k < ndest ? dest_hi[k] : 0;
+    }
+    int grid = (int)std::min<int64_t>(sm_count() * 8, std::max<int64_t>(1, (n + kXThreads * 4 - 1) / (kXThreads * 4)));
+    unsigned* ticket = static_cast<unsigned*>(work) + 1;
+    xchg_scale_push_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(n, y, static_cast<uint64_t*>(ctrl_local), ticket, iter, world, rank,
+                                                                     x_local, offset, d, sumsq_out);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (!src_mask) return 0;
+    xchg_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<uint64_t*>(ctrl_local), iter, src_mask);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// 1 if a spin of this rank has timed out since the control block was zeroed
+int thsp_xchg_timed_out(const void* ctrl_local, int* flag_host, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    uint64_t v = 0;
+    THSP_CUDA(cudaMemcpyAsync(&v, static_cast<const uint64_t*>(ctrl_local) + kXErr, sizeof(v), cudaMemcpyDeviceToHost, as_stream(stream)));
+    THSP_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    *flag_host = v ? 1 : 0;
+    return 0;
+}
+
+}  // extern "C"

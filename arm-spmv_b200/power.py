@@ -20,6 +20,10 @@ x refresh modes
              side stream stores that slice into the other replicas while interior rows are multiplied.
   halo       column-footprint analysis: a block only needs x over [min col, max col] of its rows;
              only the parts of that range owned by other ranks are pulled.
+  xchg       the same footprint, but nothing is pulled and no collective is called: the kernel that
+             normalises y stores the pieces other ranks read straight into their replicas and raises
+             a flag; the sum of squares travels the same way (csrc/exchange.cu).  One stream, five
+             kernels per step, no host synchronisation.
 With `overlap`, rows whose columns all fall inside the own slice (interior) are multiplied while
 the refresh is still in flight; the boundary blocks wait for it.
 
@@ -143,6 +147,58 @@ class CudaOps:
             return 0, -1
         return int(c.min().item()), int(c.max().item())
 
+    # ---- flag-based exchange over peer pointers (csrc/exchange.cu) --------------------------
+    def xchg_setup(self, world, rank, group_name):
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = self.lib
+        self.xw, self.xr = world, rank
+        self.ctrl = symm_mem.empty(lib.thsp_xchg_ctrl_bytes() // 8, dtype=torch.int64, device=self.device)
+        self.ctrl.zero_()
+        self.ctrl_h = symm_mem.rendezvous(self.ctrl, group=group_name)
+        self.ctrl_ptrs = [int(self.ctrl_h.buffer_ptrs[r]) for r in range(world)]
+        self.ctrl_arr = (C.c_void_p * world)(*self.ctrl_ptrs)
+        self.work = torch.zeros(lib.thsp_xchg_work_bytes() // 4, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize()
+        self.ctrl_h.barrier()
+
+    def xchg_dests(self, dests, x_peer_ptrs):
+        """dests = [(rank, lo, hi)]: pieces of this rank's slice that other ranks read."""
+        n = len(dests)
+        self.nd = n
+        self.d_x = (C.c_void_p * max(n, 1))(*[x_peer_ptrs[r] for r, _, _ in dests])
+        self.d_ctrl = (C.c_void_p * max(n, 1))(*[self.ctrl_ptrs[r] for r, _, _ in dests])
+        self.d_lo = (C.c_int64 * max(n, 1))(*[lo for _, lo, _ in dests])
+        self.d_hi = (C.c_int64 * max(n, 1))(*[hi for _, _, hi in dests])
+
+    def sumsq_publish(self, y, it):
+        self.check(self.lib.thsp_xchg_sumsq_publish_f64(C.c_int64(y.numel()), self.ptr(y), C.c_uint64(it), self.xw, self.xr, self.ctrl_arr,
+                                                        self.ptr(self.work), self.stream()))
+
+    def scale_push(self, y, it, x, offset, ss):
+        self.check(self.lib.thsp_xchg_scale_push_f64(C.c_int64(y.numel()), self.ptr(y), C.c_uint64(it), self.xw, self.xr,
+                                                     C.c_void_p(self.ctrl_ptrs[self.xr]), self.ptr(self.work), self.ptr(x), C.c_int64(offset),
+                                                     self.nd, self.d_x, self.d_ctrl, self.d_lo, self.d_hi, self.ptr(ss), self.stream()))
+
+    def wait_halo(self, it, src_mask):
+        if it > 0 and src_mask:
+            self.check(self.lib.thsp_xchg_wait(C.c_void_p(self.ctrl_ptrs[self.xr]), C.c_uint64(it), C.c_uint(src_mask), self.stream()))
+
+    def xchg_timed_out(self):
+        f = C.c_int(0)
+        self.check(self.lib.thsp_xchg_timed_out(C.c_void_p(self.ctrl_ptrs[self.xr]), C.byref(f), self.stream()))
+        return bool(f.value)
+
+
+def pushes_from_needs(all_needs, rank):
+    """all_needs[r] = [(owner, lo, hi)] of rank r (PartitionedCSR.needed_ranges).  Returns the pieces of
+    `rank`'s slice that other ranks read, one bounding range per reader: [(reader, lo, hi)]."""
+    out = []
+    for r, needs in enumerate(all_needs):
+        mine = [(lo, hi) for owner, lo, hi in needs if owner == rank and r != rank]
+        if mine:
+            out.append((r, min(a for a, _ in mine), max(b for _, b in mine)))
+    return out
+
 
 class PartitionedCSR:
     """This rank's rows of a square matrix, as a list of RowBlocks (interior first is not required)."""
@@ -211,7 +267,10 @@ class PowerIteration:
         self.y = ops.empty(A.count)
         self.ss = ops.scalar()
         self.symm = None
-        if self.world > 1 and exchange in ("fused", "push", "halo"):
+        if self.world > 1 and exchange in ("fused", "push", "halo", "xchg") and hasattr(ops, "symmetric_x"):
+            self.x = ops.symmetric_x(A.N)     # CPU test ops: plain memory, exchanges emulated over gloo
+            self.peer_ptrs = None
+        elif self.world > 1 and exchange in ("fused", "push", "halo", "xchg"):
             import torch.distributed._symmetric_memory as symm_mem
             self.x = symm_mem.empty(A.N, dtype=torch.float64, device=ops.device)
             self.symm = symm_mem.rendezvous(self.x, group=dist.group.WORLD.group_name if group is None else group.group_name)
@@ -221,6 +280,17 @@ class PowerIteration:
             self.peer_ptrs = None
         self.comm_stream = torch.cuda.Stream(device=ops.device) if (self.world > 1 and ops.device.type == "cuda") else None
         self.x_ready = None  # event: remote parts of x are fresh
+        self.iter = 0
+        if self.world > 1 and exchange == "xchg":
+            pg = dist.group.WORLD if group is None else group
+            ops.xchg_setup(self.world, self.rank, getattr(pg, "group_name", ""))
+            needs = A.needed_ranges()
+            all_needs = [None] * self.world
+            dist.all_gather_object(all_needs, needs, group=group)
+            ops.xchg_dests(pushes_from_needs(all_needs, self.rank), self.peer_ptrs)
+            self.src_mask = 0
+            for owner, _, _ in needs:
+                self.src_mask |= 1 << owner
         self.equal_split = A.N % self.world == 0
         self._init_x(seed)
 
@@ -238,6 +308,8 @@ class PowerIteration:
     # ---- one iteration ------------------------------------------------------------------
     def step(self):
         A, ops = self.A, self.ops
+        if self.world > 1 and self.exchange == "xchg":
+            return self._step_xchg()
         cur = torch.cuda.current_stream() if self.comm_stream is not None else None
         if self.world > 1 and self.overlap:
             A.spmv(ops, self.x, self.y, boundary=False)      # needs only the own slice of x
@@ -250,6 +322,23 @@ class PowerIteration:
         if self.world > 1:
             dist.all_reduce(self.ss, group=self.group)        # 8 bytes
         self._scale_and_refresh(cur)
+
+    def _step_xchg(self):
+        """One stream, no collective: interior rows | wait for the neighbours' pieces of the previous
+        step | boundary rows | partial sum published to all ranks | normalise + push the pieces the
+        neighbours read."""
+        A, ops = self.A, self.ops
+        k = self.iter + 1
+        if self.overlap:
+            A.spmv(ops, self.x, self.y, boundary=False)
+            ops.wait_halo(k - 1, self.src_mask)
+            A.spmv(ops, self.x, self.y, boundary=True)
+        else:
+            ops.wait_halo(k - 1, self.src_mask)
+            A.spmv(ops, self.x, self.y)
+        ops.sumsq_publish(self.y, k)
+        ops.scale_push(self.y, k, self.x, A.start, self.ss)
+        self.iter = k
 
     def _wait_refresh(self, cur):
         if self.x_ready is not None and cur is not None:
@@ -314,6 +403,8 @@ class PowerIteration:
 
     def norm(self) -> float:
         """||A x|| of the last step (the power-iteration eigenvalue estimate), on the host."""
+        if self.world > 1 and self.exchange == "xchg" and hasattr(self.ops, "xchg_timed_out") and self.ops.xchg_timed_out():
+            raise RuntimeError("flag-based exchange: a wait on a peer gave up (peer stalled or died)")
         return math.sqrt(float(self.ss.item()))
 
     def bytes_per_step(self) -> int:

@@ -200,6 +200,29 @@ THSP_API int thsp_scale_broadcast_f64(int64_t n, const double* src, const double
 /* sum of squares of y into *out_dev (device scalar), deterministic; = vec_dot(y,y). */
 THSP_API int thsp_sumsq_dev_f64(int64_t n, const double* y, double* out_dev, thsp_stream_t stream);
 
+/* ------------------------- power-iteration step fused with its exchange (NVLink) ------ */
+/* The vector half of y = A x; s = vec_dot(y,y); x = vec_axpby(1/sqrt(s), y, 0, y) (src/vec_vec.cpp:15-53)
+ * for row blocks on several GPUs (src/mat_vec.cpp:230-297), with no collective call: producers store
+ * into the peers' memory and raise a flag, consumers wait on the flag (csrc/exchange.cu).
+ * ctrl = thsp_xchg_ctrl_bytes() of zeroed memory per rank that every rank can address (peer
+ * pointers); work = thsp_xchg_work_bytes() of zeroed private device memory. iter counts from 1. */
+THSP_API int thsp_xchg_ctrl_bytes(void);
+THSP_API int thsp_xchg_work_bytes(void);
+/* partial sum of y_i^2 of this rank (fixed order) -> slot [iter&1][rank] of every rank's ctrl */
+THSP_API int thsp_xchg_sumsq_publish_f64(int64_t n, const double* y, uint64_t iter, int world, int rank,
+                                         void* const* peer_ctrl, void* work, thsp_stream_t stream);
+/* waits for all partials of `iter`, adds them in rank order, x[offset+i] = y[i]/sqrt(sum) into the
+ * local replica and into dest_x[d] where dest_lo[d] <= offset+i < dest_hi[d]; then raises the
+ * "halo from `rank`" flag in dest_ctrl[d].  *sumsq_out (device, may be NULL) = the sum. */
+THSP_API int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int world, int rank, void* ctrl_local,
+                                      void* work, double* x_local, int64_t offset, int ndest, double* const* dest_x,
+                                      void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi,
+                                      double* sumsq_out, thsp_stream_t stream);
+/* stream-ordered wait until the ranks in src_mask have raised their halo flag for `iter` */
+THSP_API int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stream_t stream);
+/* *flag_host = 1 if a wait of this rank gave up (~15 s) instead of hanging the GPU */
+THSP_API int thsp_xchg_timed_out(const void* ctrl_local, int* flag_host, thsp_stream_t stream);
+
 /* --------------------------------------------------------- synthetic inputs --------- */
 /* SURVEY.md 8(d).  Device-side generators (the big configs cannot go through a .mtx file);
  * oracle/oracle.c carries CPU twins that produce identical arrays. */

@@ -100,6 +100,53 @@ def test_csr_stream_ragged_alignment(thsp, cuda, oracle):
         assert_bits(y, oracle.csr_spmv(nrow, ncol, rp, ci, va, x, y0), f"ragged trial {trial}")
 
 
+def _merge_edge_lens(which, rs):
+    R = 496  # merge steps per warp-run (kMbRun = 31 lane blocks of 16 entries)
+    if which == "lane_aligned":      # every row ends exactly at a lane boundary
+        return np.full(3000, 16)
+    if which == "run_aligned":       # row + its end = exactly one run
+        return np.full(200, R - 1)
+    if which == "run_aligned_512":   # the same for the shared-memory variant (512 steps per run)
+        return np.full(200, 511)
+    if which == "empty_stretches":   # thousands of empty rows around one long row, then short rows
+        return np.concatenate([np.zeros(5000, int), [3000], np.zeros(7000, int), rs.randint(0, 4, 2000), np.zeros(1500, int)])
+    if which == "single_entry":
+        return np.array([0, 0, 1, 0])
+    if which == "mixed":
+        return rs.choice([0, 0, 0, 1, 2, 15, 16, 17, 40, 495, 496, 497, 511, 512, 513, 700], 4000)
+    if which == "one_long_row":
+        return np.array([100000])
+    if which == "all_empty_but_last":
+        return np.concatenate([np.zeros(20000, int), [5]])
+    raise KeyError(which)
+
+
+@pytest.mark.parametrize("which", ["lane_aligned", "run_aligned", "run_aligned_512", "empty_stretches", "single_entry", "mixed", "one_long_row",
+                                   "all_empty_but_last"])
+@pytest.mark.parametrize("accumulate", [True, False])
+def test_csr_merge_path_edges(thsp, cuda, oracle, which, accumulate):
+    """Merge-path kernel: rows ending on lane / run boundaries, long stretches of empty rows, rows spanning
+    many runs; through the stateless entry point and through the plan (cached run table)."""
+    from arm_spmv_b200 import host as H
+    rs = np.random.RandomState(11)
+    lens = np.asarray(_merge_edge_lens(which, rs), dtype=np.int64)
+    nrow = len(lens); ncol = 777
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nnz = int(rp[-1])
+    ci = rs.randint(0, ncol, nnz).astype(np.int32); va = rs.uniform(-1, 1, nnz)
+    x = rs.uniform(0, 1, ncol); y0 = rs.uniform(-1, 1, nrow)
+    ref = oracle.csr_spmv(nrow, ncol, rp, ci, va, x, y0 if accumulate else np.zeros(nrow))
+    scale = row_scale_csr(nrow, rp, ci, va, x)
+    y = run_csr(thsp, MERGE, 1, nrow, ncol, rp, ci, va, x, y0, accumulate)
+    assert max_row_error(y, ref, scale, y0 if accumulate else None) <= TOL64
+    A = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=dev(rp), col_ind=dev(ci), values=dev(va))
+    thsp.lib.check(thsp.load().thsp_csr_plan_set_kernel(A.plan(), MERGE, 1))
+    for _ in range(2):   # second call reuses the cached run table
+        xv, yv = H.Vector(x), H.Vector(y0.copy())
+        H.CSRMatrixMatVector(A, xv, yv, accumulate)
+        assert max_row_error(host(yv.values), ref, scale, y0 if accumulate else None) <= TOL64
+
+
 def test_csr_plan_picks_kernel_from_histogram(thsp, cuda, oracle):
     from arm_spmv_b200 import host as H
     nrow, ncol, rp, ci, va = synthetic(oracle, "stencil12")

@@ -56,6 +56,42 @@ class OracleOps:
         ci = payload[3]
         return (int(ci.min()), int(ci.max())) if len(ci) else (0, -1)
 
+    # ---- the flag-based exchange (csrc/exchange.cu), emulated with gloo collectives: what is
+    # tested here is the host logic - who pushes which piece of x to whom, and in which order
+    def symmetric_x(self, n):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def xchg_setup(self, world, rank, group_name):
+        self.xw, self.xr = world, rank
+
+    def xchg_dests(self, dests, x_peer_ptrs):
+        self.dests = dests
+
+    def wait_halo(self, it, src_mask):
+        pass   # the emulated push below is synchronous
+
+    def sumsq_publish(self, y, it):
+        self.partial = self.O.dot(y.numpy(), y.numpy())
+
+    def scale_push(self, y, it, x, offset, ss):
+        parts = [None] * self.xw
+        dist.all_gather_object(parts, self.partial)
+        tot = 0.0
+        for p in parts:          # rank order, like xchg_scale_push_kernel
+            tot += p
+        ss[0] = tot
+        w = torch.from_numpy(self.O.axpby(1.0 / np.sqrt(tot), y.numpy(), 0.0, y.numpy()))
+        x[offset:offset + y.numel()] = w
+        msgs = [(r, lo, hi, x[lo:hi].clone()) for r, lo, hi in self.dests]
+        for lo_hi in msgs:
+            assert offset <= lo_hi[1] and lo_hi[2] <= offset + y.numel(), "a rank may only push pieces of its own slice"
+        allm = [None] * self.xw
+        dist.all_gather_object(allm, msgs)
+        for src, ms in enumerate(allm):
+            for r, lo, hi, data in ms:
+                if r == self.xr:
+                    x[lo:hi] = data
+
 
 def serial_power_iteration(O, n, steps, seed):
     N = n ** 3
@@ -84,19 +120,22 @@ def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
         it = power.PowerIteration(A, ops, exchange=mode, overlap=overlap, seed=5)
         for _ in range(steps):
             it.step()
-        # after the last refresh every replica must hold the same, complete x
-        torch.save({"x": it.x.clone(), "norm": it.norm(), "start": A.start, "count": A.count,
+        # after the last refresh every replica must hold the same, complete x (xchg: only the pieces it reads)
+        torch.save({"x": it.x.clone(), "norm": it.norm(), "start": A.start, "count": A.count, "needs": A.needed_ranges(),
                     "blocks": [(b.row0, b.nrow, b.boundary) for b in A.blocks]}, f"{out}.{rank}")
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,overlap,generic", [(2, 6, True, False), (2, 7, False, False), (3, 5, True, False), (2, 6, True, True)])
-def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, overlap, generic):
+@pytest.mark.parametrize("world,n,overlap,generic,mode", [(2, 6, True, False, "allgather"), (2, 7, False, False, "allgather"),
+                                                          (3, 5, True, False, "allgather"), (2, 6, True, True, "allgather"),
+                                                          (2, 6, True, False, "xchg"), (3, 5, True, False, "xchg"),
+                                                          (3, 6, False, True, "xchg")])
+def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, overlap, generic, mode):
     steps = 4
-    port = 29500 + (os.getpid() + world * 7 + n) % 400
+    port = 29500 + (os.getpid() + world * 7 + n + len(mode)) % 400
     out = str(tmp_path / "res")
-    mp.spawn(_worker, args=(world, port, n, steps, "allgather", overlap, generic, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, steps, mode, overlap, generic, out), nprocs=world, join=True)
     x_ref, nrm_ref = serial_power_iteration(oracle, n, steps, 5)
     covered = 0
     for r in range(world):
@@ -104,6 +143,12 @@ def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, 
         assert res["start"] == covered
         covered += res["count"]
         # rows are multiplied in the reference's order, so only the norm (a sum over ranks) differs in rounding
+        if mode == "xchg":   # a replica is refreshed only where this rank reads it: own slice + needed pieces
+            xs = res["x"].numpy()
+            for lo, hi in [(res["start"], res["start"] + res["count"])] + [(a, b) for _, a, b in res["needs"]]:
+                assert np.max(np.abs(xs[lo:hi] - x_ref[lo:hi])) <= 1e-13
+            assert abs(res["norm"] - nrm_ref) <= 1e-12 * nrm_ref
+            continue
         assert np.max(np.abs(res["x"].numpy() - x_ref)) <= 1e-13
         assert abs(res["norm"] - nrm_ref) <= 1e-12 * nrm_ref
         rows = sum(b[1] for b in res["blocks"])
@@ -128,6 +173,15 @@ def test_stencil_row_blocks_cover_and_flag_boundaries(oracle):
                 needs_remote = cols.min() < start or cols.max() >= start + count
                 assert bnd or not needs_remote, (n, world, rank, r0, r1)   # interior pieces never read remote x
             assert at == start + count
+
+
+def test_pushes_are_the_transpose_of_needs():
+    sys.path.insert(0, ROOT)
+    from arm_spmv_b200 import power
+    needs = [[(1, 10, 14)], [(0, 6, 10), (2, 20, 23)], [(1, 15, 20), (1, 11, 12)]]
+    assert power.pushes_from_needs(needs, 0) == [(1, 6, 10)]
+    assert power.pushes_from_needs(needs, 1) == [(0, 10, 14), (2, 11, 20)]   # one bounding range per reader
+    assert power.pushes_from_needs(needs, 2) == [(1, 20, 23)]
 
 
 def test_partition_matches_reference_rule(oracle):
