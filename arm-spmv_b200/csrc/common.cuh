@@ -150,6 +150,34 @@ __device__ __forceinline__ double2 ld_stream2_ef(const double* p, uint64_t pol)
     asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+// 256-bit loads (sm_100: LDG.E.256): a lane takes a whole 32-byte sector in one request.
+struct int8v { int v[8]; };
+struct double4v { double v[4]; };
+struct float8v { float v[8]; };
+__device__ __forceinline__ int8v ld_stream8_ef(const int* p, uint64_t pol)
+{
+    int8v r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float8v ld_stream8_ef(const float* p, uint64_t pol)
+{
+    float8v r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+        : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double4v ld_stream4_ef(const double* p, uint64_t pol)
+{
+    double4v r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+        : "l"(p), "l"(pol));
+    return r;
+}
 // x gathers: read-only path, allocate in L1 (neighbouring rows hit the same lines).
 template <typename T>
 __device__ __forceinline__ T ld_gather(const T* p) { return __ldg(p); }

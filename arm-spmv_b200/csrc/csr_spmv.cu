@@ -497,25 +497,27 @@ static constexpr int kMbRun = 31 * kMbIPT;
 static constexpr int kMbPad = 32 * (kMbIPT + 1);
 
 template <bool kVec>
-__device__ __forceinline__ void mb_load8(const int* p, int limit, int (&c)[8], uint64_t pol)
+__device__ __forceinline__ void mb_load8(const int* p, int limit, int* c, uint64_t pol)
 {
-    // limit = entries readable from p
+    // limit = entries readable from p; kVec: p is 32-byte aligned
     if (kVec && limit >= 8) {
-        const int4 a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
-        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        const int8v a = ld_stream8_ef(p, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = a.v[k];
     } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) c[k] = k < limit ? ld_stream_ef(p + k, pol) : 0;
     }
 }
 template <bool kVec>
-__device__ __forceinline__ void mb_load8(const double* p, int limit, double (&v)[8], uint64_t pol)
+__device__ __forceinline__ void mb_load8(const double* p, int limit, double* v, uint64_t pol)
 {
     if (kVec && limit >= 8) {
+        const double4v a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            const double2 a = ld_stream2_ef(p + k, pol);
-            v[k] = a.x; v[k + 1] = a.y;
+        for (int k = 0; k < 4; ++k) {
+            v[k] = a.v[k];
+            v[k + 4] = b.v[k];
         }
     } else {
 #pragma unroll
@@ -523,19 +525,20 @@ __device__ __forceinline__ void mb_load8(const double* p, int limit, double (&v)
     }
 }
 template <bool kVec>
-__device__ __forceinline__ void mb_load8(const float* p, int limit, float (&v)[8], uint64_t pol)
+__device__ __forceinline__ void mb_load8(const float* p, int limit, float* v, uint64_t pol)
 {
     if (kVec && limit >= 8) {
-        const float4 a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        const float8v a = ld_stream8_ef(p, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = a.v[k];
     } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.f;
     }
 }
 
-template <typename V, bool kVec, bool kNoAlloc>
-__global__ void __launch_bounds__(kMergeWarps * 32, 8)
+template <typename V, bool kVec, int kB>   // kB entries of a lane in flight at once: 8 (64 registers, 8 CTAs/SM) or 16
+__global__ void __launch_bounds__(kMergeWarps * 32, kB == 8 ? 8 : 5)
     csr_merge_blocked_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                              const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y,
                              const int* __restrict__ part_row, const int* __restrict__ part_ent, int* __restrict__ carry_row,
@@ -556,10 +559,13 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     const bool mine = ks < ke;
     const int sb = lane * (kMbIPT + 1);
 
-    // the lane's first eight column indices are requested before anything else
+    // the lane's first column indices are requested before anything else
     const uint64_t pol = policy_evict_first();   // the streams are read once: keep L2 for x
-    int cc[8];
-    if (mine) mb_load8<kVec>(col + eb, nnz - eb, cc, pol);
+    int cc[kB];
+    if (mine) {
+#pragma unroll
+        for (int b = 0; b < kB; b += 8) mb_load8<kVec>(col + eb + b, nnz - eb - b, cc + b, pol);
+    }
     // ---- row starts inside the run -> marks ---------------------------------------------
     for (int q = lane; q < kMbPad; q += 32) s_mark[q] = -1;
     __syncwarp();
@@ -594,18 +600,22 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     V sum = V(0), head = V(0);
     bool has_mark = false, head_any = false, any = false;
 #pragma unroll
-    for (int h = 0; h < kMbIPT; h += 8) {
-        V xx[8], vv[8];
+    for (int h = 0; h < kMbIPT; h += kB) {
+        V xx[kB], vv[kB];
         if (mine) {
-            if (h > 0) mb_load8<kVec>(col + eb + h, nnz - eb - h, cc, pol);
+            if (h > 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const bool ok = h + k >= ks && h + k < ke;
-                xx[k] = ok ? (kNoAlloc ? ld_gather_na(x + cc[k]) : ld_gather(x + cc[k])) : V(0);
+                for (int b = 0; b < kB; b += 8) mb_load8<kVec>(col + eb + h + b, nnz - eb - h - b, cc + b, pol);
             }
-            mb_load8<kVec>(val + eb + h, nnz - eb - h, vv, pol);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < kB; ++k) {
+                const bool ok = h + k >= ks && h + k < ke;
+                xx[k] = ok ? ld_gather(x + cc[k]) : V(0);
+            }
+#pragma unroll
+            for (int b = 0; b < kB; b += 8) mb_load8<kVec>(val + eb + h + b, nnz - eb - h - b, vv + b, pol);
+#pragma unroll
+            for (int k = 0; k < kB; ++k) {
                 if (h + k >= ks && h + k < ke) {
                     const int m = s_mark[sb + h + k];
                     if (m >= 0) {
@@ -688,8 +698,8 @@ __global__ void zero_kernel(int64_t n, V* __restrict__ y)
     if (i < n) y[i] = V(0);
 }
 
-// THSP_MERGE_VARIANT (tuning): 0 = register-blocked, L1-allocating gathers (default), 1 = same with
-// non-allocating gathers, 2 / 3 = shared-memory transpose with L1-allocating / non-allocating gathers.
+// THSP_MERGE_VARIANT (tuning): 0 = register-blocked, 8 entries of a lane in flight (default), 1 = 16 in
+// flight, 2 / 3 = shared-memory transpose with L1-allocating / non-allocating gathers.
 static int merge_variant()
 {
     static const int v = getenv("THSP_MERGE_VARIANT") ? atoi(getenv("THSP_MERGE_VARIANT")) : 0;
@@ -732,17 +742,17 @@ static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* 
     const int grid = div_up(nruns, kMergeWarps), block = kMergeWarps * 32;
     const int* pr = part;
     const int* pe = part + nruns + 1;
-    const bool vec = ((((uintptr_t)val) | ((uintptr_t)col)) & 15) == 0;   // 128-bit loads of whole lane blocks
+    const bool vec = ((((uintptr_t)val) | ((uintptr_t)col)) & 31) == 0;   // 256-bit loads of whole sectors
     switch (merge_variant()) {
         case 2: csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
         case 3: csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
         case 1:
-            if (vec) csr_merge_blocked_kernel<V, true, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-            else csr_merge_blocked_kernel<V, false, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            if (vec) csr_merge_blocked_kernel<V, true, 16><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            else csr_merge_blocked_kernel<V, false, 16><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
             break;
         default:
-            if (vec) csr_merge_blocked_kernel<V, true, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-            else csr_merge_blocked_kernel<V, false, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            if (vec) csr_merge_blocked_kernel<V, true, 8><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+            else csr_merge_blocked_kernel<V, false, 8><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
     }
     THSP_LAUNCH_CHECK();
     csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y);

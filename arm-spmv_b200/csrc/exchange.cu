@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kXThreads) xchg_sumsq_publish_kernel(int64_t n
     if (!last) return;
     __threadfence();
     double tot = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kXThreads) tot = add_rn(tot, part[i]);   // fixed order per thread
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kXThreads) tot = add_rn(tot, __ldcg(part + i));   // fixed order per thread
     tot = block_sum_x(tot);
     if (threadIdx.x == 0) {
         *ticket = 0;

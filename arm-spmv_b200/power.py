@@ -18,6 +18,8 @@ x refresh modes
              NVLink peer pointers (torch symmetric memory): compute + "all-gather" in one kernel.
   push       the scale kernel writes the local replica only (critical path); a second kernel on the
              side stream stores that slice into the other replicas while interior rows are multiplied.
+  cepush     like push, but the copy engines move the slice (one peer-to-peer cudaMemcpyAsync per
+             replica): no SM is taken from the SpMV that runs meanwhile.
   halo       column-footprint analysis: a block only needs x over [min col, max col] of its rows;
              only the parts of that range owned by other ranks are pulled.
   xchg       the same footprint, but nothing is pulled and no collective is called: the kernel that
@@ -267,10 +269,10 @@ class PowerIteration:
         self.y = ops.empty(A.count)
         self.ss = ops.scalar()
         self.symm = None
-        if self.world > 1 and exchange in ("fused", "push", "halo", "xchg") and hasattr(ops, "symmetric_x"):
+        if self.world > 1 and exchange in ("fused", "push", "cepush", "halo", "xchg") and hasattr(ops, "symmetric_x"):
             self.x = ops.symmetric_x(A.N)     # CPU test ops: plain memory, exchanges emulated over gloo
             self.peer_ptrs = None
-        elif self.world > 1 and exchange in ("fused", "push", "halo", "xchg"):
+        elif self.world > 1 and exchange in ("fused", "push", "cepush", "halo", "xchg"):
             import torch.distributed._symmetric_memory as symm_mem
             self.x = symm_mem.empty(A.N, dtype=torch.float64, device=ops.device)
             self.symm = symm_mem.rendezvous(self.x, group=dist.group.WORLD.group_name if group is None else group.group_name)
@@ -362,6 +364,9 @@ class PowerIteration:
         if self.exchange == "push":
             self._barrier_async(cur, push=True)
             return
+        if self.exchange == "cepush":
+            self._barrier_async(cur, ce=True)
+            return
         # NCCL all-gather of the slices, in place, on the side stream
         done = torch.cuda.Event() if cur is not None else None
         if cur is not None:
@@ -375,7 +380,7 @@ class PowerIteration:
                 self.x_ready = torch.cuda.Event()
                 self.x_ready.record(self.comm_stream)
 
-    def _barrier_async(self, cur, pull=False, push=False):
+    def _barrier_async(self, cur, pull=False, push=False, ce=False):
         """Side-stream part of the refresh, so that interior rows can be multiplied meanwhile:
         `push`: store the own (already normalised) slice into every other replica over NVLink with
         one kernel, then a symmetric-memory barrier; `halo`: barrier, then pull the needed pieces
@@ -391,6 +396,13 @@ class PowerIteration:
                 others = [p for r, p in enumerate(self.peer_ptrs) if r != self.rank]
                 own = self.x[A.start:A.start + A.count]
                 self.ops.scale_into(own, self._one, self.x, A.start, peer_ptrs=others)   # x * (1/sqrt(1)) == x exactly
+            if ce:
+                A = self.A
+                own = self.x[A.start:A.start + A.count]
+                for r, p in enumerate(self.peer_ptrs):
+                    if r != self.rank:
+                        self.ops.check(self.ops.lib.thsp_memcpy_d2d(C.c_void_p(p + A.start * 8), self.ops.ptr(own), C.c_size_t(A.count * 8),
+                                                                    self.ops.stream()))
             self.symm.barrier()
             if pull:
                 for owner, lo, hi in self.A.needed_ranges():
@@ -508,6 +520,17 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
     return A, results
 
 
+MODE_NOTES = {
+    "xchg": "each rank stores the pieces of x its neighbours read, and its partial sum of squares, straight into their memory "
+            "over NVLink and raises a flag (csrc/exchange.cu); no collective call in the loop",
+    "allgather": "NCCL in-place all-gather of every slice into every replica (BASELINE.json's wording), overlapped with the interior rows",
+    "halo": "NCCL all-reduce of the scalar, then the needed pieces of x are pulled from their owners (peer copies)",
+    "cepush": "own slice copied into every replica by the copy engines (peer cudaMemcpyAsync), overlapped with the interior rows",
+    "push": "own slice stored into every replica by one kernel over NVLink peer pointers, on a side stream",
+    "fused": "the normalising kernel stores into all replicas itself",
+}
+
+
 def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
     """bench.py --gpus N under torchrun (one rank per GPU)."""
     rank = int(os.environ.get("RANK", 0))
@@ -538,9 +561,9 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
             "metric": METRIC, "value": round(flops / (ms * 1e-3) / 1e9, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "row-partitioned fp64 CSR power iteration (SpMV + sum-of-squares all-reduce + normalise + x refresh), "
+            "config": {"workload": "row-partitioned fp64 CSR power iteration (SpMV + sum of squares over all ranks + normalise + x refresh), "
                                    f"27-point stencil {n}^3 generated on device (BASELINE configs[4])",
-                       "rows": n ** 3, "nnz": nnz_total, "x_refresh": primary, "overlap": not args.no_overlap, "sms_reserved_for_refresh": args.reserve_sms,
+                       "rows": n ** 3, "nnz": nnz_total, "x_refresh": primary, "x_refresh_note": MODE_NOTES.get(primary, ""), "overlap": not args.no_overlap, "sms_reserved_for_refresh": args.reserve_sms,
                        "partition": f"equal row blocks x{world} (src/mat_vec.cpp:233)", "row_blocks_rank0": len(A.blocks),
                        "cache": "per-rank inputs larger than L2 (126 MB)", "norm": r["norm"]},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

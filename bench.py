@@ -7,8 +7,12 @@ N = 1   workload = BASELINE.json configs[1]: fp64 CSR SpMV, 27-point stencil on 
         (16.8 M rows, 449 M entries, 5.86 GB streamed per SpMV).  One step = one y += A x
         through the C ABI (thsp_csr_plan_spmv_f64) on torch's current stream.
 N > 1   workload = configs[4]: row-partitioned power iteration on 512^3 (3.61 G entries), one
-        process per GPU (torchrun), x replicated; one step = SpMV + ||y|| all-reduce + scale +
-        all-gather of x.  Fixed total problem -> "scaling": "strong".
+        process per GPU (torchrun), x replicated; one step = SpMV + sum of squares over all ranks +
+        normalise + refresh of the replicas of x.  Every x-refresh mode of arm-spmv_b200/power.py
+        is timed (all give bit-identical y); `value` is the first of --exchange that works - by
+        default the flag-based NVLink exchange (csrc/exchange.cu), with the NCCL all-gather of the
+        whole vector and the others beside it under "x_refresh_modes".  Fixed total problem ->
+        "scaling": "strong".
 
 `value` is GFLOP/s (2 nnz per SpMV) with everything resident in HBM; `e2e` is the same metric
 through the host-buffer C-ABI call (pinned x in, y out, copies inside the timed region);
@@ -363,7 +367,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=20)
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="N>1: SMs the interior SpMV leaves free for the concurrent NCCL all-gather (-1 = 16*log2(N): 16/32/48)")
-    ap.add_argument("--exchange", default="allgather,push,fused,halo", help="x refresh modes to time at N>1; the first that works is `value`")
+    ap.add_argument("--exchange", default="xchg,allgather,halo,cepush,push,fused",
+                    help="x refresh modes to time at N>1; the first that works is `value`")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap interior rows with the x refresh")
     ap.add_argument("--iterated-grid", type=int, default=512, help="N=1: also time the power-iteration loop on this grid (0 = skip)")
     args = ap.parse_args()
