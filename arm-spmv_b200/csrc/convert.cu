@@ -27,7 +27,7 @@ namespace thsp {
 
 // =========================================================== exclusive scan (int32) =======
 static constexpr int kScanThreads = 256;
-static constexpr int kScanItems = 4;
+static constexpr int kScanItems = 4;   // diag_flags() loads them as one int4
 static constexpr int kScanTile = kScanThreads * kScanItems;  // 1024
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* total)
@@ -394,23 +394,36 @@ __global__ void __launch_bounds__(256) sorted_check_kernel(int n, const int* __r
 // empty rows) are queued in shared memory and filled by the whole CTA with coalesced stores; all
 // gaps together are nbuckets stores.  No atomics - the earlier atomic histogram serialised on
 // hub rows (3.7 ms on the R-MAT matrix).
+static constexpr int kBndItems = 4;
 __global__ void __launch_bounds__(256) boundaries_kernel(int n, int nbuckets, const int* __restrict__ key, int* __restrict__ ptr)
 {
-    __shared__ int q_lo[256], q_hi[256], q_pos[256];
+    __shared__ int q_lo[256 * kBndItems], q_hi[256 * kBndItems], q_pos[256 * kBndItems];
     __shared__ int q_n;
     if (threadIdx.x == 0) q_n = 0;
     __syncthreads();
-    const int64_t p64 = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p64 <= n) {
-        const int p = (int)p64;
-        const int prev = p == 0 ? -1 : ld_stream(key + p - 1);
-        const int cur = p == n ? nbuckets : ld_stream(key + p);
-        const int lo = max(prev + 1, 0), hi = min(cur, nbuckets);   // fill ptr[lo..hi]
-        if (hi - lo >= 8) {
-            const int q = atomicAdd(&q_n, 1);
-            q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = p;
+    // positions p0 .. p0+3 of this thread; position n (one past the end) closes the last buckets
+    const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kBndItems;
+    if (p0 <= n) {
+        int k[kBndItems + 1];   // k[0] = key[p0-1], k[1+j] = key[p0+j]
+        k[0] = p0 == 0 ? -1 : ld_stream(key + p0 - 1);
+        if (p0 + kBndItems <= n && (((uintptr_t)key) & 15) == 0) {
+            const int4 v = ld_stream4(key + p0);
+            k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
         } else {
-            for (int r = lo; r <= hi; ++r) ptr[r] = p;
+#pragma unroll
+            for (int j = 0; j < kBndItems; ++j) k[1 + j] = p0 + j < n ? ld_stream(key + p0 + j) : nbuckets;
+        }
+#pragma unroll
+        for (int j = 0; j < kBndItems; ++j) {
+            const int64_t p = p0 + j;
+            if (p > n) break;
+            const int lo = max(k[j] + 1, 0), hi = min(k[1 + j], nbuckets);   // fill ptr[lo..hi] with p
+            if (hi - lo >= 8) {
+                const int q = atomicAdd(&q_n, 1);
+                q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = (int)p;
+            } else {
+                for (int r = lo; r <= hi; ++r) ptr[r] = (int)p;
+            }
         }
     }
     __syncthreads();
@@ -433,7 +446,7 @@ static int keys_unsorted(int n, const int* key, int* unsorted_host, cudaStream_t
 
 static int bucket_pointers(int nbuckets, int n, const int* sorted_key, int* ptr, cudaStream_t s)
 {
-    boundaries_kernel<<<div_up((int64_t)n + 1, 256), 256, 0, s>>>(n, nbuckets, sorted_key, ptr);
+    boundaries_kernel<<<div_up((int64_t)n + 1, 256 * kBndItems), 256, 0, s>>>(n, nbuckets, sorted_key, ptr);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -478,15 +491,27 @@ __global__ void __launch_bounds__(256) max_len_kernel(int nrow, const int* __res
 }
 
 // ---- packed diagonal: stable compaction of entries with row == col --------------------------
+__device__ __forceinline__ void diag_flags(int n, int base, const int* __restrict__ ri, const int* __restrict__ ci, bool (&f)[kScanItems])
+{
+    // four consecutive entries per thread: one 128-bit load per index array when the arrays allow it
+    if (base + kScanItems <= n && ((((uintptr_t)ri) | ((uintptr_t)ci)) & 15) == 0) {
+        const int4 r = ld_stream4(ri + base), c = ld_stream4(ci + base);
+        f[0] = r.x == c.x; f[1] = r.y == c.y; f[2] = r.z == c.z; f[3] = r.w == c.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) f[i] = base + i < n && ri[base + i] == ci[base + i];
+    }
+}
 __global__ void __launch_bounds__(kScanThreads) diag_count_kernel(int n, const int* __restrict__ ri, const int* __restrict__ ci,
                                                                   int* __restrict__ bcnt)
 {
     __shared__ int tot;
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    bool f[kScanItems];
+    diag_flags(n, base, ri, ci, f);
     int s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-        if (base + i < n) s += (ri[base + i] == ci[base + i]);
+    for (int i = 0; i < kScanItems; ++i) s += f[i];
     block_exclusive_scan(s, &tot);
     if (threadIdx.x == 0) bcnt[blockIdx.x] = tot;
 }
@@ -497,12 +522,10 @@ __global__ void __launch_bounds__(kScanThreads) diag_scatter_kernel(int n, const
     __shared__ int tot;
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     bool f[kScanItems];
+    diag_flags(n, base, ri, ci, f);
     int s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-        f[i] = base + i < n && ri[base + i] == ci[base + i];
-        s += f[i];
-    }
+    for (int i = 0; i < kScanItems; ++i) s += f[i];
     int pos = block_exclusive_scan(s, &tot) + boff[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i)

@@ -307,34 +307,38 @@ static StreamCfg default_stream_cfg(int nrow, int nnz)
 
 // ========================================================================= MERGE ==========
 // Merge-path CSR (Merrill & Garland): the list of row ends (row_ptr[1..nrow]) and the list of entry
-// indices (0..nnz-1) are merged conceptually; every warp gets one RUN of kMergeRun consecutive
-// steps of that merge, whatever the row lengths are - a run holds at most kMergeRun entries and
-// at most kMergeRun row ends, so neither a hub row nor a stretch of empty rows unbalances it.
+// indices (0..nnz-1) are merged conceptually; every warp gets one RUN of kMbRun consecutive steps
+// of that merge, whatever the row lengths are - a run holds at most kMbRun entries and at most
+// kMbRun row ends, so neither a hub row nor a stretch of empty rows unbalances it.
 //   0. merge_partition_kernel: the (row, entry) coordinate where each run starts (binary search
 //      along the run's diagonal).  Part of the plan; the stateless entry point recomputes it.
-//   1. the run's col_ind / val are read with coalesced streaming loads (L2 evict-first, so that
-//      the stream does not push x out of L2), kMergeU gathers of x in flight per lane, and the
-//      products are parked in shared memory in a lane-blocked, padded layout;
-//   2. every row that STARTS inside the run scatters its id to mark[start - j0] (atomicMax, so of
-//      several empty rows starting at one entry the last - the non-empty one - wins);
-//   3. lane l then owns kMergeIPT CONSECUTIVE entries: it adds them left to right, closing a row
-//      at every mark.  Rows that lie inside one lane are added into y directly.  The piece before
-//      a lane's first mark (head) and after its last (tail) belong to rows that cross lanes: one
-//      segmented warp scan over the tails gives every lane the sum carried in from the lanes to
-//      its left; the lane that holds the row's end adds carry + head into y;
-//   4. the row in which the run STARTED, if it began in an earlier run, goes to carry slot 2t;
+//   1. every row that STARTS inside the run scatters its id to mark[start - first entry]
+//      (atomicMax, so of several empty rows starting at one entry the last - the non-empty one -
+//      wins): 2 KB of shared memory per warp, the only shared memory the kernel uses;
+//   2. lane l owns 16 CONSECUTIVE entries and fetches them itself: 256-bit loads of col_ind and
+//      val (LDG.E.256: one whole 32-byte sector per request, L2 evict-first so that the stream
+//      does not push x out of L2), eight gathers of x in flight, products added left to right,
+//      a row closed at every mark.  Rows that lie inside one lane are added into y directly.  The
+//      piece before a lane's first mark (head) and after its last (tail) belong to rows that
+//      cross lanes: one segmented warp scan over the tails gives every lane the sum carried in
+//      from the lanes to its left; the lane that holds the row's end adds carry + head into y;
+//   3. the row in which the run STARTED, if it began in an earlier run, goes to carry slot 2t;
 //      whatever is still open when the run ends goes to carry slot 2t+1.
 // The fix-up pass adds the carry partials of each row in slot (= entry) order.  Rows written
 // directly and rows completed by the fix-up are disjoint: no atomics on y, deterministic.
-// Summation order: left to right inside a lane's kMergeIPT entries; lanes combined by a
-// Hillis-Steele segmented scan; run partials added left to right by the fix-up.
-static constexpr int kMergeIPT = 16;                      // entries owned by a lane
-static constexpr int kMergeRun = 32 * kMergeIPT;          // merge steps per warp-run
+// Summation order: left to right inside a lane's 16 entries; lanes combined by a Hillis-Steele
+// segmented scan; run partials added left to right by the fix-up.
+// Why the products stay in registers: on B200 the shared-memory carve-out and L1 are one 256 KB
+// array, and the lines of outstanding gather misses live in L1.  Two earlier versions of this
+// kernel staged the run through ~200 KB of shared memory per SM (coalesced loads + transpose)
+// and ran at 4.6 ms on the R-MAT matrix with DRAM at 11 %; this one takes 1.95 ms
+// (profiles/r01_ncu_rmat_kernels.txt).  Lane blocks are aligned to absolute multiples of 16
+// entries, so a run of 496 merge steps, widened to whole blocks, still fits 32 lanes; entries of
+// a block outside the run are masked.
 static constexpr int kMergeWarps = 4;                     // warps per CTA (independent of each other)
-static constexpr int kMergePad = kMergeRun + kMergeRun / kMergeIPT;   // lane stride kMergeIPT+1: conflict-free
-static constexpr int kMergeU = 8;                         // x gathers in flight per lane
-
-__device__ __forceinline__ int merge_slot(int q) { return q + q / kMergeIPT; }
+static constexpr int kMbIPT = 16;                         // entries owned by a lane
+static constexpr int kMbRun = 31 * kMbIPT;                // merge steps per warp-run
+static constexpr int kMbPad = 32 * (kMbIPT + 1);          // mark array; lane stride 17 words: conflict-free
 
 __global__ void __launch_bounds__(256) merge_partition_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, int nruns,
                                                               int run_len, int* __restrict__ part_row, int* __restrict__ part_ent)
@@ -352,149 +356,6 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(int nrow, int nnz,
     part_row[t] = lo;
     part_ent[t] = (int)(d - lo);
 }
-
-template <typename V, bool kNoAlloc>
-__global__ void __launch_bounds__(kMergeWarps * 32, 8)
-    csr_merge_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ col, const V* __restrict__ val,
-                     const V* __restrict__ x, V* __restrict__ y, const int* __restrict__ part_row,
-                     const int* __restrict__ part_ent, int* __restrict__ carry_row, V* __restrict__ carry_val, int nruns)
-{
-    __shared__ V s_prod_all[kMergeWarps][kMergePad];
-    __shared__ int s_mark_all[kMergeWarps][kMergePad];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int run = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
-    if (run >= nruns) return;  // warp-uniform; no CTA-wide barriers below
-    V* s_prod = s_prod_all[threadIdx.x >> 5];
-    int* s_mark = s_mark_all[threadIdx.x >> 5];
-    const int i0 = __ldg(part_row + run), i1 = __ldg(part_row + run + 1);
-    const int j0 = __ldg(part_ent + run), j1 = __ldg(part_ent + run + 1);
-    const int n = j1 - j0;  // entries of this run, <= kMergeRun
-    const uint64_t pol = policy_evict_first();
-    const int* colp = col + j0;
-    const V* valp = val + j0;
-
-    // ---- 1+2. stream the run, gather x, park the products; meanwhile mark the row starts -----
-    int cc[kMergeU];
-#pragma unroll
-    for (int u = 0; u < kMergeU; ++u) {
-        const int q = u * 32 + lane;
-        cc[u] = q < n ? ld_stream_ef(colp + q, pol) : 0;
-    }
-    for (int q = lane; q < kMergePad; q += 32) s_mark[q] = -1;
-    __syncwarp();
-    for (int rb = i0 + 1; rb <= i1; rb += 32) {
-        const int r = rb + lane;
-        if (r <= i1) {
-            const int s = __ldg(row_ptr + r);      // >= j0 by construction of the partition
-            if (s < j1) atomicMax(&s_mark[merge_slot(s - j0)], r);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kMergeIPT; k += kMergeU) {
-        V xx[kMergeU], vv[kMergeU];
-#pragma unroll
-        for (int u = 0; u < kMergeU; ++u) xx[u] = ((k + u) * 32 + lane < n) ? (kNoAlloc ? ld_gather_na(x + cc[u]) : ld_gather(x + cc[u])) : V(0);
-#pragma unroll
-        for (int u = 0; u < kMergeU; ++u) vv[u] = ((k + u) * 32 + lane < n) ? ld_stream_ef(valp + (k + u) * 32 + lane, pol) : V(0);
-        if (k + kMergeU < kMergeIPT) {
-#pragma unroll
-            for (int u = 0; u < kMergeU; ++u) {
-                const int q = (k + kMergeU + u) * 32 + lane;
-                cc[u] = q < n ? ld_stream_ef(colp + q, pol) : 0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kMergeU; ++u) s_prod[merge_slot((k + u) * 32 + lane)] = mul_rn(vv[u], xx[u]);
-    }
-    __syncwarp();
-
-    // ---- 3. lane-blocked reduction ------------------------------------------------------
-    const int base = lane * kMergeIPT;
-    const int cnt = max(0, min(kMergeIPT, n - base));
-    const int sb = lane * (kMergeIPT + 1);
-    int mk[kMergeIPT];
-    int lm = -1;
-#pragma unroll
-    for (int k = 0; k < kMergeIPT; ++k) {
-        mk[k] = k < cnt ? s_mark[sb + k] : -1;
-        lm = max(lm, mk[k]);
-    }
-    // row of the lane's first entry: i0 or the last mark in the lanes to its left
-    int inc_row = lm;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(full, inc_row, d);
-        if (lane >= d) inc_row = max(inc_row, t);
-    }
-    int row_in = __shfl_up_sync(full, inc_row, 1);
-    row_in = lane == 0 ? i0 : max(i0, row_in);
-    const int open_row = max(i0, __shfl_sync(full, inc_row, 31));
-
-    int cur = row_in;
-    V sum = V(0), head = V(0);
-    bool has_mark = false, head_any = false, any = false;
-#pragma unroll
-    for (int k = 0; k < kMergeIPT; ++k) {
-        if (k < cnt) {
-            if (mk[k] >= 0) {
-                if (!has_mark) {
-                    head = sum;
-                    head_any = any;
-                    has_mark = true;
-                } else {
-                    y[cur] = add_rn(y[cur], sum);   // a row that starts and ends inside this lane
-                }
-                cur = mk[k];
-                sum = V(0);
-            }
-            sum = any || has_mark ? add_rn(sum, s_prod[sb + k]) : s_prod[sb + k];
-            any = true;
-        }
-    }
-    // segmented scan over the lanes' tails; a lane with a mark starts a new segment
-    V tail = sum;
-    bool flag = has_mark;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const V tv = __shfl_up_sync(full, tail, d);
-        const bool tf = __shfl_up_sync(full, (int)flag, d) != 0;
-        if (lane >= d) {
-            if (!flag) tail = add_rn(tv, tail);
-            flag = flag || tf;
-        }
-    }
-    const V carry_in = __shfl_up_sync(full, tail, 1);   // inclusive scan of lane-1 = what flows into this lane
-    const bool first_shared = __ldg(row_ptr + i0) < j0;
-    if (lane == 0) carry_row[2 * run] = -1;
-    __syncwarp();
-    if (has_mark && (lane > 0 || head_any)) {
-        V tot = head;
-        if (lane > 0) tot = head_any ? add_rn(carry_in, head) : carry_in;
-        if (row_in == i0 && first_shared) {
-            carry_row[2 * run] = i0;
-            carry_val[2 * run] = tot;
-        } else {
-            y[row_in] = add_rn(y[row_in], tot);
-        }
-    }
-    if (lane == 31) {
-        carry_row[2 * run + 1] = n > 0 ? open_row : -1;
-        carry_val[2 * run + 1] = tail;
-    }
-}
-
-// ---- register-blocked variant ---------------------------------------------------------------
-// Same algorithm, but a lane fetches ITS 16 consecutive entries itself (four 128-bit col_ind loads,
-// eight 128-bit val loads) instead of going through a coalesced load + shared-memory transpose:
-// the products never touch shared memory, which is left to L1 - on B200 the unified L1/shared
-// array also holds the lines of outstanding gather misses, and a kernel that fills it with staging
-// buffers starves its own gathers (measured: profiles/r01_merge_*).  Lane blocks are aligned to
-// absolute multiples of 16 entries, so a run of 496 merge steps, widened to whole blocks, still
-// fits 32 lanes; entries of a block outside the run are masked.
-static constexpr int kMbIPT = 16;
-static constexpr int kMbRun = 31 * kMbIPT;
-static constexpr int kMbPad = 32 * (kMbIPT + 1);
 
 template <bool kVec>
 __device__ __forceinline__ void mb_load8(const int* p, int limit, int* c, uint64_t pol)
@@ -537,9 +398,10 @@ __device__ __forceinline__ void mb_load8(const float* p, int limit, float* v, ui
     }
 }
 
-template <typename V, bool kVec, int kB>   // kB entries of a lane in flight at once: 8 (64 registers, 8 CTAs/SM) or 16
-__global__ void __launch_bounds__(kMergeWarps * 32, kB == 8 ? 8 : 5)
-    csr_merge_blocked_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
+static constexpr int kB = 8;   // entries of a lane in flight at once (64 registers, 8 CTAs/SM; 16 in flight measured slower)
+template <typename V, bool kVec>
+__global__ void __launch_bounds__(kMergeWarps * 32, 8)
+    csr_merge_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                              const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y,
                              const int* __restrict__ part_row, const int* __restrict__ part_ent, int* __restrict__ carry_row,
                              V* __restrict__ carry_val, int nruns)
@@ -698,25 +560,13 @@ __global__ void zero_kernel(int64_t n, V* __restrict__ y)
     if (i < n) y[i] = V(0);
 }
 
-// THSP_MERGE_VARIANT (tuning): 0 = register-blocked, 8 entries of a lane in flight (default), 1 = 16 in
-// flight, 2 / 3 = shared-memory transpose with L1-allocating / non-allocating gathers.
-static int merge_variant()
-{
-    static const int v = getenv("THSP_MERGE_VARIANT") ? atoi(getenv("THSP_MERGE_VARIANT")) : 0;
-    return v;
-}
-static inline int merge_run_len() { return merge_variant() >= 2 ? kMergeRun : kMbRun; }
-static inline int merge_runs(int nrow, int nnz)
-{
-    const int len = merge_run_len();
-    return (int)(((int64_t)nrow + nnz + len - 1) / len);
-}
+static inline int merge_runs(int nrow, int nnz) { return (int)(((int64_t)nrow + nnz + kMbRun - 1) / kMbRun); }
 
 // part = nruns+1 row coordinates followed by nruns+1 entry coordinates
 static int merge_partition(int nrow, int nnz, const int* rp, int* part, cudaStream_t s)
 {
     const int nruns = merge_runs(nrow, nnz);
-    merge_partition_kernel<<<div_up(nruns + 1, 256), 256, 0, s>>>(nrow, nnz, rp, nruns, merge_run_len(), part, part + nruns + 1);
+    merge_partition_kernel<<<div_up(nruns + 1, 256), 256, 0, s>>>(nrow, nnz, rp, nruns, kMbRun, part, part + nruns + 1);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -743,17 +593,8 @@ static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* 
     const int* pr = part;
     const int* pe = part + nruns + 1;
     const bool vec = ((((uintptr_t)val) | ((uintptr_t)col)) & 31) == 0;   // 256-bit loads of whole sectors
-    switch (merge_variant()) {
-        case 2: csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
-        case 3: csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, rp, col, val, x, y, pr, pe, crow, cval, nruns); break;
-        case 1:
-            if (vec) csr_merge_blocked_kernel<V, true, 16><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-            else csr_merge_blocked_kernel<V, false, 16><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-            break;
-        default:
-            if (vec) csr_merge_blocked_kernel<V, true, 8><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-            else csr_merge_blocked_kernel<V, false, 8><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-    }
+    if (vec) csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+    else csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
     THSP_LAUNCH_CHECK();
     csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y);
     THSP_LAUNCH_CHECK();

@@ -14,12 +14,12 @@
 //                                 in CTA order, stores the rank's partial into slot [parity][rank]
 //                                 of EVERY rank's control block, then the iteration number into
 //                                 the matching flag.
-//   thsp_xchg_scale_push_f64      waits until the flags of all ranks show this iteration, adds the
-//                                 partials in rank order (every rank gets the same bits),
-//                                 x_own = y / sqrt(sum) into the local replica and, for the index
-//                                 ranges other ranks read, into their replicas as well; when all
-//                                 CTAs are done the last one raises the "halo from <rank>" flag
-//                                 on those ranks.
+//   thsp_xchg_scale_push_f64      one warp waits until the flags of all ranks show this iteration
+//                                 (lane r on rank r) and adds the partials in rank order - every
+//                                 rank gets the same bits; then x_own = y / sqrt(sum) goes into the
+//                                 local replica and, for the index ranges other ranks read, into
+//                                 their replicas as well; when all CTAs are done the last one
+//                                 raises the "halo from <rank>" flag on those ranks.
 //   thsp_xchg_wait                one thread spins until the halo flags of the given source ranks
 //                                 show the iteration; launched in front of the rows that read
 //                                 remote parts of x.
@@ -111,13 +111,33 @@ __global__ void __launch_bounds__(kXThreads) xchg_sumsq_publish_kernel(int64_t n
     double tot = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += kXThreads) tot = add_rn(tot, __ldcg(part + i));   // fixed order per thread
     tot = block_sum_x(tot);
-    if (threadIdx.x == 0) {
-        *ticket = 0;
+    if (threadIdx.x < 32) {
+        // lane p talks to rank p: value, one system-scope fence, then the flag (a fence orders the
+        // lane's earlier store before its later one for every observer - no release needed per flag)
+        tot = __shfl_sync(0xffffffffu, tot, 0);
         const int par = (int)(iter & 1);
-        for (int p = 0; p < world; ++p) st_relaxed_sys(peers.ctrl[p] + kXPart + par * kXMaxRanks + rank, (uint64_t)__double_as_longlong(tot));
+        const int p = threadIdx.x;
+        if (p == 0) *ticket = 0;
+        if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPart + par * kXMaxRanks + rank, (uint64_t)__double_as_longlong(tot));
         __threadfence_system();
-        for (int p = 0; p < world; ++p) st_release_sys(peers.ctrl[p] + kXPartFlag + par * kXMaxRanks + rank, iter);
+        if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPartFlag + par * kXMaxRanks + rank, iter);
     }
+}
+
+// One warp: lane r waits for rank r's partial of this iteration; the partials are then added in
+// rank order (every rank gets the same bits) and the sum lands in *sumsq_out for the scale kernel.
+__global__ void xchg_reduce_kernel(uint64_t* ctrl, uint64_t iter, int world, double* __restrict__ sumsq_out)
+{
+    const int r = threadIdx.x;
+    const int par = (int)(iter & 1);
+    double v = 0.0;
+    if (r < world) {
+        spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
+        v = __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r));
+    }
+    double tot = 0.0;
+    for (int k = 0; k < world; ++k) tot = add_rn(tot, __shfl_sync(0xffffffffu, v, k));
+    if (r == 0) *sumsq_out = tot;
 }
 
 struct XDests {
@@ -127,42 +147,34 @@ struct XDests {
     int n;
 };
 
-__global__ void __launch_bounds__(kXThreads) xchg_scale_push_kernel(int64_t n, const double* __restrict__ y, uint64_t* ctrl,
-                                                                    unsigned* __restrict__ ticket, uint64_t iter, int world, int rank,
+__global__ void __launch_bounds__(kXThreads) xchg_scale_push_kernel(int64_t n, const double* __restrict__ y,
+                                                                    unsigned* __restrict__ ticket, uint64_t iter, int rank,
                                                                     double* __restrict__ x_local, int64_t offset, XDests dst,
-                                                                    double* __restrict__ sumsq_out)
+                                                                    const double* __restrict__ sumsq)
 {
-    __shared__ double s_inv;
     __shared__ bool last;
-    if (threadIdx.x == 0) {
-        const int par = (int)(iter & 1);
-        double tot = 0.0;
-        for (int r = 0; r < world; ++r) {   // rank order: the same bits on every rank
-            spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
-            tot = add_rn(tot, __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r)));
-        }
-        s_inv = 1.0 / sqrt(tot);
-        if (blockIdx.x == 0 && sumsq_out) *sumsq_out = tot;
-    }
-    __syncthreads();
-    const double inv = s_inv;
+    const double inv = 1.0 / sqrt(*sumsq);
     const int64_t stride = (int64_t)gridDim.x * kXThreads;
+    bool remote = false;
     for (int64_t i = (int64_t)blockIdx.x * kXThreads + threadIdx.x; i < n; i += stride) {
         const double v = mul_rn(inv, y[i]);   // vec_axpby's beta == 0 branch: w = alpha * x
         const int64_t g = offset + i;
         x_local[g] = v;
         for (int d = 0; d < dst.n; ++d)
-            if (g >= dst.lo[d] && g < dst.hi[d]) dst.x[d][g] = v;
+            if (g >= dst.lo[d] && g < dst.hi[d]) {
+                dst.x[d][g] = v;
+                remote = true;
+            }
     }
     if (dst.n == 0) return;
-    __threadfence_system();   // this thread's remote stores are visible before the ticket
+    if (remote) __threadfence_system();   // this thread's remote stores are visible before the ticket
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        *ticket = 0;
+    if (last && threadIdx.x < 32) {
+        if (threadIdx.x == 0) *ticket = 0;
         __threadfence_system();
-        for (int d = 0; d < dst.n; ++d) st_release_sys(dst.ctrl[d] + kXHalo + rank, iter);
+        if ((int)threadIdx.x < dst.n) st_relaxed_sys(dst.ctrl[threadIdx.x] + kXHalo + rank, iter);
     }
 }
 
@@ -196,6 +208,8 @@ int thsp_xchg_sumsq_publish_f64(int64_t n, const double* y, uint64_t iter, int w
     grid = std::min(grid, sm_count() * 8);
     unsigned* ticket = static_cast<unsigned*>(work);
     double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
+    static bool hinted = false;
+    prefer_max_shared(xchg_sumsq_publish_kernel, &hinted);
     xchg_sumsq_publish_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(n, y, part, ticket, iter, world, rank, pe);
     THSP_LAUNCH_CHECK();
     return 0;
@@ -208,6 +222,7 @@ int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int worl
     if (ensure_device()) return 1;
     THSP_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "bad world / rank");
     THSP_REQUIRE(ndest >= 0 && ndest < kXMaxRanks, "too many destinations");
+    THSP_REQUIRE(sumsq_out != nullptr, "sumsq_out is the device scalar the sum is handed over in");
     XDests d;
     d.n = ndest;
     for (int k = 0; k < kXMaxRanks; ++k) {
@@ -216,10 +231,15 @@ int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int worl
         d.lo[k] = k < ndest ? dest_lo[k] : 0;
         d.hi[k] = k < ndest ? dest_hi[k] : 0;
     }
+    cudaStream_t s = as_stream(stream);
+    static bool hinted[2] = {false, false};
+    prefer_max_shared(xchg_reduce_kernel, &hinted[0]);
+    prefer_max_shared(xchg_scale_push_kernel, &hinted[1]);
+    xchg_reduce_kernel<<<1, 32, 0, s>>>(static_cast<uint64_t*>(ctrl_local), iter, world, sumsq_out);
+    THSP_LAUNCH_CHECK();
     int grid = (int)std::min<int64_t>(sm_count() * 8, std::max<int64_t>(1, (n + kXThreads * 4 - 1) / (kXThreads * 4)));
     unsigned* ticket = static_cast<unsigned*>(work) + 1;
-    xchg_scale_push_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(n, y, static_cast<uint64_t*>(ctrl_local), ticket, iter, world, rank,
-                                                                     x_local, offset, d, sumsq_out);
+    xchg_scale_push_kernel<<<grid, kXThreads, 0, s>>>(n, y, ticket, iter, rank, x_local, offset, d, sumsq_out);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -228,6 +248,8 @@ int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stre
 {
     if (ensure_device()) return 1;
     if (!src_mask) return 0;
+    static bool hinted = false;
+    prefer_max_shared(xchg_wait_kernel, &hinted);
     xchg_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<uint64_t*>(ctrl_local), iter, src_mask);
     THSP_LAUNCH_CHECK();
     return 0;

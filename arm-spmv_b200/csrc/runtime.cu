@@ -1,5 +1,6 @@
 // runtime.cu -- device selection, memory, error text, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -32,6 +33,12 @@ int ensure_device()
         return 1;
     }
     return 0;
+}
+
+bool carveout_hint_enabled()
+{
+    static const bool on = !(getenv("THSP_CARVEOUT") && atoi(getenv("THSP_CARVEOUT")) == 0);
+    return on;
 }
 
 static constexpr int kMaxDev = 16;

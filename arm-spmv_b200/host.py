@@ -269,6 +269,51 @@ def csr_spmv_kernel(kernel: int, lanes: int, A: CSRMatrix, x: torch.Tensor, y: t
              1 if accumulate else 0, current_stream()))
 
 
+# ---- include/data_io.h:12 : Matrix Market reader ----------------------------------------------
+class MatrixMarketNeedsScanf(ValueError):
+    """The entry section holds something the GPU parser's fast conversions do not cover."""
+
+
+def mtx_split(path: str):
+    """Banner, comments and size line of a coordinate file (what mmio does on the CPU in the reference,
+    src/mmio.cpp:109-229) -> (nrow, ncol, nnz, bytes of the entry section)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = 0
+    first = True
+    while True:
+        end = data.find(b"\n", pos)
+        line = data[pos:] if end < 0 else data[pos:end]
+        nxt = len(data) if end < 0 else end + 1
+        if first:
+            if not line.lower().startswith(b"%%matrixmarket"):
+                raise ValueError("*** Could not process Matrix Market banner ***")
+            words = line.lower().split()
+            if len(words) >= 4 and words[1] == b"matrix" and words[2] == b"coordinate" and words[3] == b"complex":
+                raise ValueError("Sorry, this application does not support Market Market type: [" + b" ".join(words[1:]).decode() + "]")
+            first = False
+        elif line.strip() and not line.startswith(b"%"):
+            rows, cols, nz = (int(v) for v in line.split()[:3])
+            return rows, cols, nz, data[nxt:]
+        if end < 0:
+            raise ValueError("no size line")
+        pos = nxt
+
+
+def COOMatrixRead(path: str, device=None) -> COOMatrix:
+    """COOMatrixRead (src/data_io.cpp:45-105) with the entry loop (:83-88) on the GPU (thsp_mtx_parse_coo)."""
+    rows, cols, nz, body = mtx_split(path)
+    dev = _dev(device)
+    ri = torch.empty(nz, dtype=I32, device=dev)
+    ci = torch.empty(nz, dtype=I32, device=dev)
+    va = torch.empty(nz, dtype=F64, device=dev)
+    status = C.c_int(1)
+    check(load().thsp_mtx_parse_coo(C.c_char_p(body), C.c_size_t(len(body)), nz, ptr(ri), ptr(ci), ptr(va), C.byref(status), current_stream()))
+    if status.value != 0:
+        raise MatrixMarketNeedsScanf(path)
+    return COOMatrix(rows, cols, ri, ci, va)
+
+
 # ---- synthetic inputs (SURVEY.md 8(d)) ------------------------------------------------------
 def stencil27_csr(n: int, row_begin: int = 0, row_end: int | None = None, device=None) -> CSRMatrix:
     N = n ** 3

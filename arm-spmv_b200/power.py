@@ -283,6 +283,7 @@ class PowerIteration:
         self.comm_stream = torch.cuda.Stream(device=ops.device) if (self.world > 1 and ops.device.type == "cuda") else None
         self.x_ready = None  # event: remote parts of x are fresh
         self.iter = 0
+        self.trace = None    # list of (phase name, event) when tracing (PowerIteration.trace_on)
         if self.world > 1 and exchange == "xchg":
             pg = dist.group.WORLD if group is None else group
             ops.xchg_setup(self.world, self.rank, getattr(pg, "group_name", ""))
@@ -313,17 +314,44 @@ class PowerIteration:
         if self.world > 1 and self.exchange == "xchg":
             return self._step_xchg()
         cur = torch.cuda.current_stream() if self.comm_stream is not None else None
+        self._mark("start")
         if self.world > 1 and self.overlap:
             A.spmv(ops, self.x, self.y, boundary=False)      # needs only the own slice of x
+            self._mark("interior rows")
             self._wait_refresh(cur)
+            self._mark("wait for refresh")
             A.spmv(ops, self.x, self.y, boundary=True)
+            self._mark("boundary rows")
         else:
             self._wait_refresh(cur)
             A.spmv(ops, self.x, self.y)
+            self._mark("all rows")
         ops.sumsq(self.y, self.ss)
+        self._mark("sum of squares")
         if self.world > 1:
             dist.all_reduce(self.ss, group=self.group)        # 8 bytes
+            self._mark("all-reduce")
         self._scale_and_refresh(cur)
+        self._mark("scale (+ refresh launch)")
+
+    # ---- phase trace: where an iteration's time goes (CUDA events on the main stream) -----------
+    def trace_on(self):
+        self.trace = []
+
+    def _mark(self, name):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.trace.append((name, e))
+
+    def trace_report(self):
+        """Mean milliseconds between consecutive marks, keyed by the phase that ENDS at the mark."""
+        torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (_, e0), (name, e1) in zip(self.trace[:-1], self.trace[1:]):
+            acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+            cnt[name] = cnt.get(name, 0) + 1
+        return {k: acc[k] / cnt[k] for k in acc}
 
     def _step_xchg(self):
         """One stream, no collective: interior rows | wait for the neighbours' pieces of the previous
@@ -331,15 +359,22 @@ class PowerIteration:
         neighbours read."""
         A, ops = self.A, self.ops
         k = self.iter + 1
+        self._mark("start")
         if self.overlap:
             A.spmv(ops, self.x, self.y, boundary=False)
+            self._mark("interior rows")
             ops.wait_halo(k - 1, self.src_mask)
+            self._mark("wait for neighbours")
             A.spmv(ops, self.x, self.y, boundary=True)
+            self._mark("boundary rows")
         else:
             ops.wait_halo(k - 1, self.src_mask)
             A.spmv(ops, self.x, self.y)
+            self._mark("all rows")
         ops.sumsq_publish(self.y, k)
+        self._mark("sum of squares + publish")
         ops.scale_push(self.y, k, self.x, A.start, self.ss)
+        self._mark("reduce + scale + push")
         self.iter = k
 
     def _wait_refresh(self, cur):
@@ -471,6 +506,7 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
     ops = CudaOps(device)
     A = PartitionedCSR.stencil27(n, rank, world, ops)
     results = {}
+    sync_token = torch.zeros(1, device=device)
     for mode in modes:
         try:
             it = PowerIteration(A, ops, exchange=mode, overlap=overlap, reserve_sms=reserve_sms)
@@ -486,6 +522,11 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = launch_count()
         with ClockSampler(device.index or 0) as clk:
+            if world > 1:
+                # The host threads leave the barrier above milliseconds apart; a collective queued on the
+                # stream right before the first event lines the GPUs up, so the timed region holds the
+                # `steps` iterations and not the launch skew of the slowest host thread.
+                dist.all_reduce(sync_token)
             e0.record()
             for _ in range(steps):
                 it.step()
@@ -498,6 +539,14 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         results[mode] = {"ms_per_step": float(ms.item()), "norm": it.norm(), "launches": int(launches), "clocks": clk.summary(),
                          "bytes_per_step_rank": it.bytes_per_step()}
+        if os.environ.get("THSP_POWER_TRACE"):   # where the time goes, rank by rank (a separate, untimed run)
+            it.trace_on()
+            for _ in range(10):
+                it.step()
+            rep = it.trace_report()
+            results[mode]["phases_ms"] = {k: round(v, 4) for k, v in rep.items()}
+            print(f"[trace rank {rank} {mode}] " + "  ".join(f"{k}: {v:.3f}" for k, v in rep.items()), flush=True)
+            it.trace = None
         if with_e2e and "e2e" not in results:
             xh = torch.empty(A.count, dtype=torch.float64).pin_memory()
             yh = torch.empty(A.count, dtype=torch.float64).pin_memory()

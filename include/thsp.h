@@ -200,6 +200,16 @@ THSP_API int thsp_scale_broadcast_f64(int64_t n, const double* src, const double
 /* sum of squares of y into *out_dev (device scalar), deterministic; = vec_dot(y,y). */
 THSP_API int thsp_sumsq_dev_f64(int64_t n, const double* y, double* out_dev, thsp_stream_t stream);
 
+/* ------------------------------------------------ Matrix Market entries on the GPU --- */
+/* The entry loop of COOMatrixRead (src/data_io.cpp:83-88: fscanf("%d %d %lg\n") per entry, indices
+ * made 0-based).  text_host[0, len) = the bytes of the file after the size line (host memory);
+ * row_ind / col_ind / val = device or managed arrays of nnz entries.  The values are the correctly
+ * rounded doubles strtod would return.  *status = 0: parsed here.  *status = 1: the text holds
+ * something the fast conversions do not cover (inf/nan, hex floats, more than 19 significant
+ * digits, malformed or missing tokens, 4 GB or more) - outputs undefined, run the scanf loop. */
+THSP_API int thsp_mtx_parse_coo(const char* text_host, size_t len, int nnz, int* row_ind, int* col_ind, double* val,
+                                int* status, thsp_stream_t stream);
+
 /* ------------------------- power-iteration step fused with its exchange (NVLink) ------ */
 /* The vector half of y = A x; s = vec_dot(y,y); x = vec_axpby(1/sqrt(s), y, 0, y) (src/vec_vec.cpp:15-53)
  * for row blocks on several GPUs (src/mat_vec.cpp:230-297), with no collective call: producers store
@@ -213,7 +223,7 @@ THSP_API int thsp_xchg_sumsq_publish_f64(int64_t n, const double* y, uint64_t it
                                          void* const* peer_ctrl, void* work, thsp_stream_t stream);
 /* waits for all partials of `iter`, adds them in rank order, x[offset+i] = y[i]/sqrt(sum) into the
  * local replica and into dest_x[d] where dest_lo[d] <= offset+i < dest_hi[d]; then raises the
- * "halo from `rank`" flag in dest_ctrl[d].  *sumsq_out (device, may be NULL) = the sum. */
+ * "halo from `rank`" flag in dest_ctrl[d].  *sumsq_out (device scalar, required) = the sum. */
 THSP_API int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int world, int rank, void* ctrl_local,
                                       void* work, double* x_local, int64_t offset, int ndest, double* const* dest_x,
                                       void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi,
