@@ -50,19 +50,6 @@ void* scratch(size_t bytes, int slot);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Kernels that run between two launches of the persistent SpMV kernels (which take the whole
-// shared-memory carve-out) ask for the same carve-out, so that the SMs do not have to re-split
-// their L1/shared array twice per iteration.  These kernels stream and have no use for L1.
-// THSP_CARVEOUT=0 turns the hint off (tuning).
-bool carveout_hint_enabled();
-template <typename K>
-static inline void prefer_max_shared(K kernel, bool* done)
-{
-    if (*done) return;   // per process is enough: the attribute belongs to the function, set on each device it is first used on
-    if (carveout_hint_enabled()) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    *done = true;
-}
-
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -208,8 +208,6 @@ int thsp_xchg_sumsq_publish_f64(int64_t n, const double* y, uint64_t iter, int w
     grid = std::min(grid, sm_count() * 8);
     unsigned* ticket = static_cast<unsigned*>(work);
     double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
-    static bool hinted = false;
-    prefer_max_shared(xchg_sumsq_publish_kernel, &hinted);
     xchg_sumsq_publish_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(n, y, part, ticket, iter, world, rank, pe);
     THSP_LAUNCH_CHECK();
     return 0;
@@ -232,9 +230,6 @@ int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int worl
         d.hi[k] = k < ndest ? dest_hi[k] : 0;
     }
     cudaStream_t s = as_stream(stream);
-    static bool hinted[2] = {false, false};
-    prefer_max_shared(xchg_reduce_kernel, &hinted[0]);
-    prefer_max_shared(xchg_scale_push_kernel, &hinted[1]);
     xchg_reduce_kernel<<<1, 32, 0, s>>>(static_cast<uint64_t*>(ctrl_local), iter, world, sumsq_out);
     THSP_LAUNCH_CHECK();
     int grid = (int)std::min<int64_t>(sm_count() * 8, std::max<int64_t>(1, (n + kXThreads * 4 - 1) / (kXThreads * 4)));
@@ -248,8 +243,6 @@ int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stre
 {
     if (ensure_device()) return 1;
     if (!src_mask) return 0;
-    static bool hinted = false;
-    prefer_max_shared(xchg_wait_kernel, &hinted);
     xchg_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(static_cast<uint64_t*>(ctrl_local), iter, src_mask);
     THSP_LAUNCH_CHECK();
     return 0;

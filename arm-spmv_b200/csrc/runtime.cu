@@ -35,12 +35,6 @@ int ensure_device()
     return 0;
 }
 
-bool carveout_hint_enabled()
-{
-    static const bool on = !(getenv("THSP_CARVEOUT") && atoi(getenv("THSP_CARVEOUT")) == 0);
-    return on;
-}
-
 static constexpr int kMaxDev = 16;
 int sm_count()
 {

@@ -100,9 +100,6 @@ static int dot_to_device(int64_t n, const double* x, const double* y, double* ou
     int grid = ew_grid(n > 0 ? n : 1);
     double* part = static_cast<double*>(scratch(sizeof(double) * (size_t)grid, 0));
     if (!part) return 1;
-    static bool hinted[2] = {false, false};
-    prefer_max_shared(dot_partial_kernel, &hinted[0]);
-    prefer_max_shared(sum_final_kernel, &hinted[1]);
     dot_partial_kernel<<<grid, kRedThreads, 0, s>>>(n, x, y, part);
     THSP_LAUNCH_CHECK();
     sum_final_kernel<<<1, kRedThreads, 0, s>>>(grid, part, out_dev);
@@ -255,8 +252,6 @@ int thsp_scale_broadcast_f64(int64_t n, const double* src, const double* sumsq_d
     PeerList pl;
     for (int k = 0; k < 8; ++k) pl.p[k] = k < npeers ? peer_dst[k] : nullptr;
     if (n <= 0) return 0;
-    static bool hinted = false;
-    prefer_max_shared(scale_broadcast_kernel, &hinted);
     scale_broadcast_kernel<<<ew_grid(n), kEwThreads, 0, as_stream(stream)>>>(n, src, sumsq_dev, pl, npeers, offset);
     THSP_LAUNCH_CHECK();
     return 0;
