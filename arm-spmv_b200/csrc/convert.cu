@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(int n, const 
                                                                    int* __restrict__ counts, int nblk)
 {
     __shared__ int wcnt[kRadixWarps][256];
-    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < kRadixWarps; ++i) wcnt[i][threadIdx.x] = 0;
@@ -235,7 +234,6 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
     __shared__ int wcnt[kRadixWarps][256];   // per-warp digit counters, later exclusive warp offsets
     __shared__ int tile_off[256];            // first position of each digit inside the sorted tile
     __shared__ int gbase[256];               // where this tile's run of each digit starts in the output
-    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int tile = blockIdx.x * kRadixTile;
     const int tile_n = min(kRadixTile, n - tile);

@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(int nrow, const int* __
         int j = rs + sub;
         // Narrow lane counts walk along cache lines over several iterations: let L1 keep them.
         // Wide ones consume whole lines per instruction: stream past L1.
-        auto ldc = [&](const int* p) { return L <= 4 ? __ldg(p) : ld_stream(p); };
-        auto ldv = [&](const V* p) { return L <= 4 ? __ldg(p) : ld_stream(p); };
+        const uint64_t pol = policy_evict_first();
+        auto ldc = [&](const int* p) { return L <= 4 ? __ldg(p) : ld_stream_ef(p, pol); };
+        auto ldv = [&](const V* p) { return L <= 4 ? __ldg(p) : ld_stream_ef(p, pol); };
         // two entries in flight per lane
         for (; j + L < re; j += 2 * L) {
             int c0 = ldc(col + j), c1 = ldc(col + j + L);

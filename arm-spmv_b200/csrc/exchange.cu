@@ -46,10 +46,6 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v)
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

@@ -198,4 +198,22 @@ int thsp_device_sync(void)
 }
 uint64_t thsp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// Scratch grows with the largest call seen (a COO->CSR of 268 M entries keeps 9.7 GB of sort buffers);
+// a caller that is done converting can hand it back.
+int thsp_scratch_release(void)
+{
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDev) return 0;
+    THSP_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (int i = 0; i < kSlots; ++i) {
+        Scratch& sc = g_scratch[dev][i];
+        if (sc.p) cudaFree(sc.p);
+        sc.p = nullptr;
+        sc.cap = 0;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -367,8 +367,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=20)
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="N>1: SMs the interior SpMV leaves free for the concurrent NCCL all-gather (-1 = 16*log2(N): 16/32/48)")
-    ap.add_argument("--exchange", default="xchg,allgather,halo,cepush,push,fused",
-                    help="x refresh modes to time at N>1; the first that works is `value`")
+    ap.add_argument("--exchange", default="xchg,allgather,halo",
+                    help="x refresh modes to time at N>1 (also: cepush, push, fused); the first that works is `value`")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap interior rows with the x refresh")
     ap.add_argument("--iterated-grid", type=int, default=512, help="N=1: also time the power-iteration loop on this grid (0 = skip)")
     args = ap.parse_args()

@@ -65,6 +65,9 @@ THSP_API int thsp_stream_sync(thsp_stream_t stream);
 THSP_API int thsp_device_sync(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 THSP_API uint64_t thsp_launch_count(void);
+/* Frees the library's scratch buffers on the current device (they grow to the largest call seen:
+ * sort buffers of a conversion, staged text of the reader).  The next call re-allocates. */
+THSP_API int thsp_scratch_release(void);
 
 /* --------------------------------------------------------------------- SpMV -------- */
 /* Kernel ids for CSR.  AUTO picks from the row-length statistics gathered by the plan. */
