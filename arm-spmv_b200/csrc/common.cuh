@@ -178,6 +178,50 @@ __device__ __forceinline__ double4v ld_stream4_ef(const double* p, uint64_t pol)
         : "l"(p), "l"(pol));
     return r;
 }
+// Eight consecutive elements of a stream into registers: one 256-bit load (two for doubles) when the
+// address is 32-byte aligned and all eight exist, guarded scalar loads otherwise.  Used by the kernels
+// whose lanes own consecutive entries (merge-path CSR, COO).
+template <bool kVec>
+__device__ __forceinline__ void load_block8(const int* p, int limit, int* c, uint64_t pol)
+{
+    // limit = entries readable from p; kVec: p is 32-byte aligned
+    if (kVec && limit >= 8) {
+        const int8v a = ld_stream8_ef(p, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = a.v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = k < limit ? ld_stream_ef(p + k, pol) : 0;
+    }
+}
+template <bool kVec>
+__device__ __forceinline__ void load_block8(const double* p, int limit, double* v, uint64_t pol)
+{
+    if (kVec && limit >= 8) {
+        const double4v a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = a.v[k];
+            v[k + 4] = b.v[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.0;
+    }
+}
+template <bool kVec>
+__device__ __forceinline__ void load_block8(const float* p, int limit, float* v, uint64_t pol)
+{
+    if (kVec && limit >= 8) {
+        const float8v a = ld_stream8_ef(p, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = a.v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.f;
+    }
+}
+
 // x gathers: read-only path, allocate in L1 (neighbouring rows hit the same lines).
 template <typename T>
 __device__ __forceinline__ T ld_gather(const T* p) { return __ldg(p); }

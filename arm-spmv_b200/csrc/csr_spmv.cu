@@ -358,47 +358,6 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(int nrow, int nnz,
     part_ent[t] = (int)(d - lo);
 }
 
-template <bool kVec>
-__device__ __forceinline__ void mb_load8(const int* p, int limit, int* c, uint64_t pol)
-{
-    // limit = entries readable from p; kVec: p is 32-byte aligned
-    if (kVec && limit >= 8) {
-        const int8v a = ld_stream8_ef(p, pol);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = a.v[k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] = k < limit ? ld_stream_ef(p + k, pol) : 0;
-    }
-}
-template <bool kVec>
-__device__ __forceinline__ void mb_load8(const double* p, int limit, double* v, uint64_t pol)
-{
-    if (kVec && limit >= 8) {
-        const double4v a = ld_stream4_ef(p, pol), b = ld_stream4_ef(p + 4, pol);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = a.v[k];
-            v[k + 4] = b.v[k];
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.0;
-    }
-}
-template <bool kVec>
-__device__ __forceinline__ void mb_load8(const float* p, int limit, float* v, uint64_t pol)
-{
-    if (kVec && limit >= 8) {
-        const float8v a = ld_stream8_ef(p, pol);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = a.v[k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = k < limit ? ld_stream_ef(p + k, pol) : 0.f;
-    }
-}
-
 static constexpr int kB = 8;   // entries of a lane in flight at once (64 registers, 8 CTAs/SM; 16 in flight measured slower)
 template <typename V, bool kVec>
 __global__ void __launch_bounds__(kMergeWarps * 32, 8)
@@ -427,7 +386,7 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     int cc[kB];
     if (mine) {
 #pragma unroll
-        for (int b = 0; b < kB; b += 8) mb_load8<kVec>(col + eb + b, nnz - eb - b, cc + b, pol);
+        for (int b = 0; b < kB; b += 8) load_block8<kVec>(col + eb + b, nnz - eb - b, cc + b, pol);
     }
     // ---- row starts inside the run -> marks ---------------------------------------------
     for (int q = lane; q < kMbPad; q += 32) s_mark[q] = -1;
@@ -468,7 +427,7 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
         if (mine) {
             if (h > 0) {
 #pragma unroll
-                for (int b = 0; b < kB; b += 8) mb_load8<kVec>(col + eb + h + b, nnz - eb - h - b, cc + b, pol);
+                for (int b = 0; b < kB; b += 8) load_block8<kVec>(col + eb + h + b, nnz - eb - h - b, cc + b, pol);
             }
 #pragma unroll
             for (int k = 0; k < kB; ++k) {
@@ -476,7 +435,7 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
                 xx[k] = ok ? ld_gather(x + cc[k]) : V(0);
             }
 #pragma unroll
-            for (int b = 0; b < kB; b += 8) mb_load8<kVec>(val + eb + h + b, nnz - eb - h - b, vv + b, pol);
+            for (int b = 0; b < kB; b += 8) load_block8<kVec>(val + eb + h + b, nnz - eb - h - b, vv + b, pol);
 #pragma unroll
             for (int k = 0; k < kB; ++k) {
                 if (h + k >= ks && h + k < ke) {

@@ -93,80 +93,59 @@ static int launch_ell(int nrow, int width, const int* col, const V* val, const V
 }
 
 // ============================================================================ COO ==========
-// One warp sweeps a contiguous run of entries, 32 per step with coalesced row/col/val loads.
-// Products of equal, ADJACENT rows are combined by a segmented warp scan; the segment that is
-// still open at the end of a step is carried into the next step in registers (carry-out), so a
-// row-sorted COO issues one red.global.add.f64 per row and run instead of one per entry.
-// Segments that close are added into y with an atomic, because an unsorted COO may hold the
-// same row anywhere else (the reference uses `omp atomic` for the same reason, :36-39).
-// Order: tree inside a step, steps chained left to right, atomics in arbitrary order - the
-// reference's own order is unspecified under OpenMP.
-static constexpr int kCooRun = 2048;  // entries per warp
+// A lane owns 16 CONSECUTIVE entries and fetches them itself: 256-bit loads of row_ind, col_ind
+// and val (LDG.E.256, one whole 32-byte sector per request, L2 evict-first), eight gathers of x
+// in flight.  It adds the products left to right while the row stays the same and hands every
+// finished run of equal rows to y with one red.global.add.f64 - an atomic, because an unsorted
+// COO may hold the same row anywhere else (the reference uses `omp atomic` for the same reason,
+// src/mat_vec.cpp:36-39).  A row-sorted COO (every generator, most .mtx files) therefore issues
+// about one atomic per 16 entries or per row, whichever is shorter; an unsorted one, one per
+// entry, and is bound by the DRAM traffic of 134 MB of x and y touched at random (2.7 ms on the
+// 8M x 8M matrix, DRAM 10.9 GB read + 2.6 GB written; evict-last hints on x and y changed nothing).
+// The earlier version combined equal adjacent rows with a segmented warp scan every 32 entries:
+// 72 % of the issue slots on the sorted 256^3 stencil (1.90 ms, profiles/r01_ncu_final_stencil.txt).
+// Order: left to right inside a lane's run, atomics in arbitrary order - the reference's own
+// order is unspecified under OpenMP.
+static constexpr int kCooIPT = 16;   // entries owned by a lane
 
+template <bool kVec>
 __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict__ row, const int* __restrict__ col,
                                                   const double* __restrict__ val, const double* __restrict__ x,
                                                   double* __restrict__ y)
 {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int64_t e0 = run * kCooRun;
-    if (e0 >= nnz) return;
-    const int e1 = (int)min((int64_t)nnz, e0 + kCooRun);
-    int open_row = -1;
-    double open_sum = 0.0;
-    // The three streams are read once: evict-first.  (Evict-last hints on the x gathers and the y
-    // reductions were tried as well and changed nothing on the unsorted 8M x 8M matrix: x and y together,
-    // 134 MB touched at random, do not fit L2 either way - 2.73 ms, DRAM 10.9 GB read + 2.6 GB written.)
+    const int64_t e64 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kCooIPT;
+    if (e64 >= nnz) return;
+    const int e = (int)e64;
+    const int n = min(kCooIPT, nnz - e);
     const uint64_t pol = policy_evict_first();
-    auto add_y = [&](int r, double v) { atomicAdd(y + r, v); };
-
-    // One 32-entry step: segmented scan, chain with the open segment, emit closed segments.
-    auto step = [&](int g, int r, double p) {
-        const int rl = __shfl_up_sync(full, r, 1);
-        const bool head = (lane == 0) || (rl != r);
-        const unsigned heads = __ballot_sync(full, head);
-        const int seg_start = 31 - __clz(heads & (full >> (31 - lane)));
+    int rr[kCooIPT];
+    load_block8<kVec>(row + e, n, rr, pol);
+    load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
+    int cur = rr[0];
+    double sum = 0.0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double q = __shfl_up_sync(full, p, d);
-            if (lane - d >= seg_start) p = add_rn(p, q);
-        }
-        const int r0 = __shfl_sync(full, r, 0);
-        if (open_row >= 0) {
-            if (r0 == open_row) {
-                if (seg_start == 0) p = add_rn(open_sum, p);
-            } else if (lane == 0) {
-                add_y(open_row, open_sum);
+    for (int h = 0; h < kCooIPT; h += 8) {
+        int cc[8];
+        double xx[8], vv[8];
+        load_block8<kVec>(col + e + h, n - h, cc, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xx[k] = h + k < n ? ld_gather(x + cc[k]) : 0.0;
+        load_block8<kVec>(val + e + h, n - h, vv, pol);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (h + k < n) {
+                const double p = mul_rn(vv[k], xx[k]);
+                if (rr[h + k] != cur) {
+                    atomicAdd(y + cur, sum);
+                    cur = rr[h + k];
+                    sum = p;
+                } else {
+                    sum = (h + k == 0) ? p : add_rn(sum, p);
+                }
             }
         }
-        const int rn = __shfl_down_sync(full, r, 1);
-        const int last = min(31, e1 - g - 1);
-        if (g + lane < e1 && lane != last && rn != r) add_y(r, p);
-        open_row = __shfl_sync(full, r, last);
-        open_sum = __shfl_sync(full, p, last);
-    };
-
-    // Four steps' worth of loads are issued before the first scan: 2 KB in flight per warp.
-    constexpr int U = 4;
-    for (int g = (int)e0; g < e1; g += 32 * U) {
-        int rr[U], cc[U];
-        double vv[U], xx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = g + u * 32 + lane;
-            const bool ok = e < e1;
-            rr[u] = ok ? ld_stream_ef(row + e, pol) : -2;
-            cc[u] = ok ? ld_stream_ef(col + e, pol) : 0;
-            vv[u] = ok ? ld_stream_ef(val + e, pol) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) xx[u] = (g + u * 32 + lane < e1) ? ld_gather(x + cc[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (g + u * 32 < e1) step(g + u * 32, rr[u], mul_rn(vv[u], xx[u]));
     }
-    if (lane == 0 && open_row >= 0) add_y(open_row, open_sum);
+    atomicAdd(y + cur, sum);
 }
 
 // ============================================================================ CSC ==========
@@ -375,8 +354,10 @@ int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int
     (void)nrow; (void)ncol;
     if (ensure_device()) return 1;
     if (nnz <= 0) return 0;
-    const int runs = div_up(nnz, kCooRun);
-    coo_kernel<<<div_up(runs, 8), 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
+    const int grid = div_up(div_up(nnz, kCooIPT), 256);
+    const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)col_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads
+    if (vec) coo_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
+    else coo_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
     THSP_LAUNCH_CHECK();
     return 0;
 }

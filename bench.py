@@ -19,7 +19,8 @@ through the host-buffer C-ABI call (pinned x in, y out, copies inside the timed 
 `roofline` is algorithmic bytes / CUDA-event time of the SpMV kernel against the measured copy
 bandwidth in MEASURED_PEAKS.json; `cpu_baseline` times the reference's own CPU code
 (oracle/_ref/libref.so, built from /root/reference; the C port in oracle/ if that is absent) on
-this box's host cores.  --impl reference prints that CPU arm as its own JSON line.
+this box's host cores.  --impl reference prints that CPU arm as its own JSON line (N = 1: the SpMV; N > 1: the
+power-iteration step composed from the reference's own calls, on 256^3 - 512^3 does not fit its int32 structs).
 """
 from __future__ import annotations
 
@@ -117,8 +118,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_arm(n, reps, warm=1):
-    """The reference's CPU CSR SpMV (main.cpp:54-61 protocol) on an n^3 27-point stencil.
+def cpu_reference_arm(n, reps, warm=1, iterated=False):
+    """The reference's CPU CSR SpMV (main.cpp:54-61 protocol) on an n^3 27-point stencil - or, with
+    `iterated`, the power-iteration step composed from the reference's own calls (Fill, CSRMatrixMatVector,
+    vec_dot, vec_axpby: SURVEY.md 3.5), which is what the N > 1 arm measures.
     Returns (gflops, seconds_per_call, kind, cores, sample)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -128,8 +131,13 @@ def cpu_reference_arm(n, reps, warm=1):
     rp, ci, va = O.gen_stencil27_csr(n)
     N = n ** 3
     x = O.gen_vector(N, 11)
+    what = "power-iteration steps (y=0; y+=Ax; sqrt(dot); axpby)" if iterated else "back-to-back y+=Ax"
     try:
         R = pyoracle.Ref()
+
+        def run(k):
+            return R.time_power_iteration(N, rp, ci, va, x, k)[0] if iterated else R.time_csr_spmv(N, N, rp, ci, va, x, k)
+
         # Give the reference every host thread that helps: containers often expose more CPUs
         # than their quota serves, and the reference's static OpenMP loop then slows down with
         # threads.  Try 1, 2, 4, ... nproc on a short run and keep the fastest.
@@ -142,25 +150,28 @@ def cpu_reference_arm(n, reps, warm=1):
         best = None
         for t in cand:
             R.set_threads(t)
-            R.time_csr_spmv(N, N, rp, ci, va, x, 1)
-            d = R.time_csr_spmv(N, N, rp, ci, va, x, 2)
+            run(1)
+            d = run(2)
             if best is None or d < best[0]:
                 best = (d, t)
         cores = best[1]
         R.set_threads(cores)
         for _ in range(warm):
-            R.time_csr_spmv(N, N, rp, ci, va, x, 1)
-        dt = R.time_csr_spmv(N, N, rp, ci, va, x, reps)
+            run(1)
+        dt = run(reps)
         kind = "reference"
     except (FileNotFoundError, OSError):
         y = np.zeros(N)
         t0 = time.perf_counter()
-        for _ in range(max(1, reps // 4)):
-            y = O.csr_spmv(N, N, rp, ci, va, x, y)
-        dt = (time.perf_counter() - t0) / max(1, reps // 4)
+        k = max(1, reps // 4)
+        for _ in range(k):
+            y = O.csr_spmv(N, N, rp, ci, va, x, np.zeros(N) if iterated else y)
+            if iterated:
+                x = O.axpby(1.0 / np.sqrt(O.dot(y, y)), y, 0.0, y)
+        dt = (time.perf_counter() - t0) / k
         kind, cores = "port", 1
     nnz = int(rp[-1])
-    sample = f"27-pt stencil {n}^3 ({N} rows, {nnz} nnz), {reps} back-to-back y+=Ax, mean"
+    sample = f"27-pt stencil {n}^3 ({N} rows, {nnz} nnz), {reps} {what}, mean"
     return 2.0 * nnz / dt / 1e9, dt, kind, cores, sample
 
 
@@ -169,16 +180,19 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.grid
-    t_all = []
-    for _ in range(max(1, args.warmup)):
-        pass  # warm-up happens inside cpu_reference_arm (one untimed call per measurement)
-    gf, dt, kind, cores, sample = cpu_reference_arm(n, max(1, args.steps))
+    multi = args.gpus > 1 or env_int("WORLD_SIZE", 1) > 1
+    gf, dt, kind, cores, sample = cpu_reference_arm(n, max(1, args.steps), warm=max(1, min(args.warmup, 2)), iterated=multi)
     N = n ** 3
+    if multi:
+        workload = (f"fp64 CSR power iteration composed from the reference's calls, 27-point stencil {n}^3, CPU reference ({kind}); "
+                    "the 512^3 matrix of the GPU arm (3.6e9 entries) does not fit the reference's int32 structs, so the sample is 256^3")
+    else:
+        workload = f"fp64 CSR SpMV, 27-point stencil {n}^3, CPU reference ({kind})"
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gf, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"fp64 CSR SpMV, 27-point stencil {n}^3, CPU reference ({kind})", "grid": n, "rows": N},
+        "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "grid": n, "rows": N},
         "cpu_baseline": {"value": round(gf, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(gf, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

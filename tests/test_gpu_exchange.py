@@ -1,0 +1,79 @@
+"""-m gpu: the flag-based exchange of the power iteration (csrc/exchange.cu) with two VIRTUAL ranks on one GPU - two
+control blocks, two replicas of x, two streams.  The kernels cannot tell peer memory from local memory, so the
+protocol (partial sums published to every rank, flags, rank-ordered reduction, pushes of the pieces the other rank
+reads, waits) runs exactly as it does over NVLink; arm-spmv_b200/power.py drives the same entry points with one
+process per GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class VirtualRank:
+    def __init__(self, lib, rank, world, n_total, start, count):
+        self.lib, self.rank, self.world, self.start, self.count = lib, rank, world, start, count
+        self.ctrl = torch.zeros(lib.thsp_xchg_ctrl_bytes() // 8, dtype=torch.int64, device="cuda")
+        self.work = torch.zeros(lib.thsp_xchg_work_bytes() // 4, dtype=torch.int32, device="cuda")
+        self.x = torch.full((n_total,), float("nan"), dtype=torch.float64, device="cuda")
+        self.ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self.stream = torch.cuda.Stream()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("n_total,halo", [(100_003, 517), (4_000_000, 70_000), (64, 64)])
+def test_two_virtual_ranks(thsp, cuda, n_total, halo):
+    from arm_spmv_b200.lib import check
+    lib = thsp.load()
+    world = 2
+    per = n_total // world
+    parts = [(0, per), (per, n_total - per)]
+    ranks = [VirtualRank(lib, r, world, n_total, *parts[r]) for r in range(world)]
+    ctrl_arr = (C.c_void_p * world)(*[r.ctrl.data_ptr() for r in ranks])
+    # rank 0 reads the first `halo` entries of rank 1's slice, rank 1 the last `halo` entries of rank 0's
+    h0 = min(halo, parts[1][1])
+    h1 = min(halo, parts[0][1])
+    dests = {0: (1, per - h1, per), 1: (0, per, per + h0)}
+    torch.cuda.synchronize()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for it in range(1, 5):
+        ys = [torch.rand(parts[r][1], dtype=torch.float64, device="cuda", generator=gen) - 0.3 for r in range(world)]
+        torch.cuda.synchronize()
+        for r in ranks:
+            with torch.cuda.stream(r.stream):
+                s = C.c_void_p(r.stream.cuda_stream)
+                check(lib.thsp_xchg_sumsq_publish_f64(C.c_int64(r.count), _p(ys[r.rank]), C.c_uint64(it), world, r.rank, ctrl_arr,
+                                                      _p(r.work), s))
+        for r in ranks:
+            with torch.cuda.stream(r.stream):
+                s = C.c_void_p(r.stream.cuda_stream)
+                other, lo, hi = dests[r.rank]
+                dx = (C.c_void_p * 1)(ranks[other].x.data_ptr())
+                dc = (C.c_void_p * 1)(ranks[other].ctrl.data_ptr())
+                dlo, dhi = (C.c_int64 * 1)(lo), (C.c_int64 * 1)(hi)
+                check(lib.thsp_xchg_scale_push_f64(C.c_int64(r.count), _p(ys[r.rank]), C.c_uint64(it), world, r.rank, _p(r.ctrl),
+                                                   _p(r.work), _p(r.x), C.c_int64(r.start), 1, dx, dc, dlo, dhi, _p(r.ss), s))
+                check(lib.thsp_xchg_wait(_p(r.ctrl), C.c_uint64(it), C.c_uint(1 << other), s))
+        torch.cuda.synchronize()
+        tot = sum(float((y.double() ** 2).sum().item()) for y in ys)
+        for r in ranks:
+            flag = C.c_int(1)
+            check(lib.thsp_xchg_timed_out(_p(r.ctrl), C.byref(flag), None))
+            assert flag.value == 0
+            assert abs(float(r.ss.item()) - tot) <= 1e-13 * tot
+        assert ranks[0].ss.item() == ranks[1].ss.item()          # every rank normalises with the same bits
+        inv = 1.0 / np.sqrt(ranks[0].ss.item())
+        for r in ranks:
+            own = r.x[r.start:r.start + r.count]
+            assert torch.equal(own, ys[r.rank] * inv)             # vec_axpby's beta == 0 branch: one multiply
+            other, lo, hi = dests[r.rank]
+            assert torch.equal(ranks[other].x[lo:hi], r.x[lo:hi])  # the pushed piece, bit for bit
+            # nothing outside [own slice + pushed piece] of the other replica was touched by this rank
+        if it == 1:
+            untouched = ranks[1].x[: per - h1]
+            assert bool(torch.isnan(untouched).all()) or untouched.numel() == 0
