@@ -135,11 +135,39 @@ __global__ void __launch_bounds__(kEwThreads) scale_broadcast_kernel(int64_t n, 
     }
 }
 
+// diag[i] = sum of the entries (i, i) of a CSR matrix (0 when the row has none), one thread per row.
+__global__ void __launch_bounds__(256) csr_diagonal_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
+                                                           const double* __restrict__ va, double* __restrict__ diag)
+{
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= nrow) return;
+    double d = 0.0;
+    for (int p = rp[r]; p < rp[r + 1]; ++p)
+        if (ci[p] == r) d = add_rn(d, va[p]);
+    diag[r] = d;
+}
+
 }  // namespace thsp
 
 using namespace thsp;
 
 extern "C" {
+
+int thsp_csr_diagonal_f64(int nrow, const int* row_ptr, const int* col_ind, const double* val, double* diag, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (nrow <= 0) return 0;
+    csr_diagonal_kernel<<<div_up(nrow, 256), 256, 0, as_stream(stream)>>>(nrow, row_ptr, col_ind, val, diag);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// x[i] += omega * r[i] / diag[i]: the update of a (damped) Jacobi sweep, r = b - A x
+int thsp_jacobi_update_f64(int64_t n, double omega, const double* diag, const double* r, double* x, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { x[i] = add_rn(x[i], mul_rn(omega, __ddiv_rn(r[i], diag[i]))); });
+}
 
 int thsp_dot_dev_f64(int64_t n, const double* x, const double* y, double* result_dev, thsp_stream_t stream)
 {

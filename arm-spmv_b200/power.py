@@ -121,6 +121,14 @@ class CudaOps:
         A.plan()
         return A, A.nnz
 
+    def csc_block(self, nrow, ncol, col_ptr, row_ind, values):
+        return self.H.CSCMatrix(nrow=nrow, ncol=ncol, col_ptr=col_ptr, row_ind=row_ind, values=values, device=self.device)
+
+    def csc_spmv(self, payload, x, y):
+        """y += A_block x through thsp_csc_spmv_f64 (x, y: torch tensors)."""
+        self.check(self.lib.thsp_csc_spmv_f64(payload.nrow, payload.ncol, payload.nnz, self.ptr(payload.col_ptr), self.ptr(payload.row_ind),
+                                              self.ptr(payload.values), self.ptr(x), self.ptr(y), self.stream()))
+
     def spmv(self, payload, x, y):
         """y = A_block x (overwrite: saves Fill(0) and the read of y)."""
         self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
@@ -483,6 +491,39 @@ class _Null:
 
     def __exit__(self, *a):
         return False
+
+
+# =========================================================================================
+class ColumnPartitionedCSC:
+    """CSC across the GPUs: what CSCMatrixMatVectorNuma does with threads
+    (src/mat_vec.cpp:299-366 - equal COLUMN blocks, column pointers rebased, a full-length private y per
+    block) plus the step the reference leaves out: the private y's are never added up there.  Here every
+    rank multiplies its column block by its slice of x into a full-length partial y, and one
+    reduce-scatter (NCCL over NVLink) leaves each rank with its slice of the sum; ranks own equal row and
+    column slices except the last, which takes the remainder (:233,245-246) - an uneven split falls back to
+    an all-reduce."""
+
+    def __init__(self, nrow: int, ncol: int, col_ptr, row_ind, values, rank: int, world: int, ops, group=None):
+        self.nrow, self.ncol, self.rank, self.world, self.ops, self.group = nrow, ncol, rank, world, ops, group
+        self.c0, self.ncol_local = partition_rows(ncol, world, rank)
+        self.r0, self.nrow_local = partition_rows(nrow, world, rank)
+        e0, e1 = int(col_ptr[self.c0]), int(col_ptr[self.c0 + self.ncol_local])
+        sub_cp = (col_ptr[self.c0:self.c0 + self.ncol_local + 1] - e0).to(torch.int32).contiguous()   # rebased, :331-334
+        self.block = ops.csc_block(nrow, self.ncol_local, sub_cp, row_ind[e0:e1].contiguous(), values[e0:e1].contiguous())
+        self.partial = ops.empty(nrow)
+        self.equal_rows = nrow % world == 0
+
+    def spmv(self, x_slice, y_slice):
+        """y_slice = (A x)[own rows]; x_slice = x[own columns]."""
+        self.partial.zero_()
+        self.ops.csc_spmv(self.block, x_slice, self.partial)     # partial += A[:, own columns] x_slice
+        if self.world == 1:
+            y_slice.copy_(self.partial)
+        elif self.equal_rows and self.partial.is_cuda:
+            dist.reduce_scatter_tensor(y_slice, self.partial, group=self.group)
+        else:
+            dist.all_reduce(self.partial, group=self.group)
+            y_slice.copy_(self.partial[self.r0:self.r0 + self.nrow_local])
 
 
 # =========================================================================================

@@ -189,6 +189,17 @@ THSP_API int thsp_add2_scaled_f64(int64_t n, double a, const double* x, double b
 THSP_API int thsp_check_vector_f64(int64_t nx, const double* x, int64_t ny, const double* y, int* ok_host,
                                    thsp_stream_t stream);
 
+/* ------------------------------------------------ callers above the path */
+/* The reference keeps a `diagonal` array "for SymGS" (include/matrix.h:36,81) and never uses it.  These two
+ * are what a smoother needs from the library; CG and Jacobi themselves are compositions of CSRMatrixMatVector,
+ * vec_dot and vec_axpby (arm-spmv_b200/solvers.py). */
+/* diag[i] = sum of the stored entries (i, i) of row i, 0 if none */
+THSP_API int thsp_csr_diagonal_f64(int nrow, const int* row_ptr, const int* col_ind, const double* val, double* diag,
+                                   thsp_stream_t stream);
+/* x[i] += omega * r[i] / diag[i] */
+THSP_API int thsp_jacobi_update_f64(int64_t n, double omega, const double* diag, const double* r, double* x,
+                                    thsp_stream_t stream);
+
 /* --------------------------------------------- row-block partition (multi-GPU) ------ */
 /* *MatVectorNuma (src/mat_vec.cpp:230-268): equal row blocks, last takes the remainder. Host-only. */
 THSP_API int thsp_partition_rows(int64_t nrow, int nparts, int part, int64_t* start, int64_t* count);

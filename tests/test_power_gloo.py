@@ -56,6 +56,13 @@ class OracleOps:
         ci = payload[3]
         return (int(ci.min()), int(ci.max())) if len(ci) else (0, -1)
 
+    def csc_block(self, nrow, ncol, col_ptr, row_ind, values):
+        return (nrow, ncol, col_ptr.numpy(), row_ind.numpy(), values.numpy())
+
+    def csc_spmv(self, payload, x, y):
+        nrow, ncol, cp, ri, va = payload
+        y.copy_(torch.from_numpy(self.O.csc_spmv(nrow, ncol, cp, ri, va, x.numpy(), y.numpy())))
+
     # ---- the flag-based exchange (csrc/exchange.cu), emulated with gloo collectives: what is
     # tested here is the host logic - who pushes which piece of x to whom, and in which order
     def symmetric_x(self, n):
@@ -173,6 +180,39 @@ def test_stencil_row_blocks_cover_and_flag_boundaries(oracle):
                 needs_remote = cols.min() < start or cols.max() >= start + count
                 assert bnd or not needs_remote, (n, world, rank, r0, r1)   # interior pieces never read remote x
             assert at == start + count
+
+
+def _csc_worker(rank, world, port, nrow, ncol, nnz, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arm_spmv_b200 import power
+        ops = OracleOps()
+        ri, cj, v = ops.O.gen_uniform_coo(nrow, ncol, nnz, 7)
+        cp, rind, va = ops.O.coo2csc(nrow, ncol, ri, cj, v)
+        A = power.ColumnPartitionedCSC(nrow, ncol, torch.from_numpy(cp), torch.from_numpy(rind), torch.from_numpy(va), rank, world, ops)
+        x = torch.from_numpy(ops.O.gen_vector(ncol, 2))
+        y = torch.zeros(A.nrow_local, dtype=torch.float64)
+        A.spmv(x[A.c0:A.c0 + A.ncol_local].clone(), y)
+        torch.save({"y": y, "r0": A.r0}, f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nrow,ncol", [(2, 300, 200), (3, 100, 301)])
+def test_column_partitioned_csc_matches_serial(oracle, tmp_path, world, nrow, ncol):
+    nnz = 4000
+    port = 29900 + (os.getpid() + world + nrow) % 90
+    out = str(tmp_path / "csc")
+    mp.spawn(_csc_worker, args=(world, port, nrow, ncol, nnz, out), nprocs=world, join=True)
+    ri, cj, v = oracle.gen_uniform_coo(nrow, ncol, nnz, 7)
+    x = oracle.gen_vector(ncol, 2)
+    ref = oracle.coo_spmv(nrow, ncol, ri, cj, v, x, np.zeros(nrow))
+    scale = np.bincount(ri, weights=np.abs(v * x[cj]), minlength=nrow)
+    got = np.concatenate([torch.load(f"{out}.{r}")["y"].numpy() for r in range(world)])
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.maximum(scale, 1e-300)) <= 1e-12
 
 
 def test_pushes_are_the_transpose_of_needs():
