@@ -76,6 +76,56 @@ def test_conversions_match_oracle_medium(thsp, cuda, oracle, kind):
         assert_bits(host(E.offsets), off, "dia off"); assert_bits(host(E.values), dv, "dia val")
 
 
+@pytest.mark.parametrize("case", ["one_entry", "one_row_hub", "one_column_hub", "tile_minus_1", "tile_exact", "tile_plus_1", "two_tiles",
+                                  "one_pass", "two_passes", "three_passes", "four_passes", "sorted_with_huge_gaps", "descending",
+                                  "all_duplicates", "empty"])
+def test_conversion_edges(thsp, cuda, oracle, case):
+    """The radix sort's corner cases against the oracle's counting sort (src/matrix.cpp:125-144), bit for bit: tile
+    boundaries (4096 entries per CTA), 1 to 4 digit passes (up to 2^25 buckets), hub buckets, long runs of empty
+    buckets in front of / between / behind the keys, already sorted and reversed input, nothing at all."""
+    from arm_spmv_b200 import host as H
+    import zlib
+    rs = np.random.RandomState(zlib.crc32(case.encode()))
+    T = 4096
+    nnz, nrow, ncol = 3 * T + 5, 5000, 4000
+    if case == "one_entry":
+        nnz = 1
+    elif case in ("tile_minus_1", "tile_exact", "tile_plus_1", "two_tiles"):
+        nnz = {"tile_minus_1": T - 1, "tile_exact": T, "tile_plus_1": T + 1, "two_tiles": 2 * T}[case]
+    elif case in ("one_pass", "two_passes", "three_passes", "four_passes"):
+        nrow = {"one_pass": 200, "two_passes": 60000, "three_passes": (1 << 17) + 3, "four_passes": (1 << 25) - 7}[case]
+        ncol = 300
+    elif case == "empty":
+        nnz = 0
+    ri = rs.randint(0, nrow, nnz).astype(np.int32)
+    ci = rs.randint(0, ncol, nnz).astype(np.int32)
+    va = rs.uniform(-1, 1, nnz)
+    if case == "one_row_hub":
+        ri[:] = 1234
+    elif case == "one_column_hub":
+        ci[:] = 77
+    elif case == "sorted_with_huge_gaps":
+        nrow = 1 << 22
+        ri = np.sort(rs.choice(np.array([5, 6, 7, 100000, 100001, 3000000, nrow - 1], dtype=np.int32), nnz)).astype(np.int32)
+    elif case == "descending":
+        ri = np.sort(ri)[::-1].copy()
+    elif case == "all_duplicates":
+        ri[:] = 3; ci[:] = 3
+    A = H.COOMatrix(nrow, ncol, ri, ci, va)
+    B = H.CSRMatrix(A); Cc = H.CSCMatrix(A)
+    rp, co, cv, dg = oracle.coo2csr(nrow, ncol, ri, ci, va)
+    assert_bits(host(B.row_ptr), rp, "row_ptr"); assert_bits(host(B.col_ind), co, "csr col"); assert_bits(host(B.values), cv, "csr val")
+    nd = min(len(dg), nrow)
+    assert_bits(host(B.diagonal)[:nd], dg[:nd], "diag")
+    cp, ro, cv2 = oracle.coo2csc(nrow, ncol, ri, ci, va)
+    assert_bits(host(Cc.col_ptr), cp, "col_ptr"); assert_bits(host(Cc.row_ind), ro, "csc row"); assert_bits(host(Cc.values), cv2, "csc val")
+    if case not in ("one_row_hub", "all_duplicates", "four_passes", "sorted_with_huge_gaps"):   # keep the ELL slab small
+        D = H.ELLMatrix(A)
+        k, eco, eva, _ = oracle.coo2ell(nrow, ncol, ri, ci, va)
+        assert D.nonzeros_in_row == k
+        assert_bits(host(D.col_ind), eco, "ell col"); assert_bits(host(D.values), eva, "ell val")
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 1023, 1024, 1025, 5000, 1024 * 1024 + 17, 3_000_001])
 def test_exclusive_scan(thsp, cuda, n):
     rs = np.random.RandomState(n % 97)
