@@ -162,17 +162,71 @@ __global__ void __launch_bounds__(256) hist_kernel(int n, const int* __restrict_
 // counts -> stable scatter.  The entries travel with their keys, so every pass reads and writes
 // whole cache lines and no random gather is left at the end (the earlier (key, index) sort spent
 // 40 % of its time gathering 12-byte payloads from random sectors: profiles/r01_conv_*).
-// A tile is 4096 consecutive entries; warp w owns entries [w*512, (w+1)*512) of it and walks them
-// in 16 rounds of 32 (coalesced loads).  Stable rank of an entry = (entries with the same digit
+//
+// Histogram: counting needs no order, so every lane keeps PRIVATE byte counters, four digits to a
+// 32-bit word, in its own shared-memory bank (word [digit/4][lane]): a load, an add and a store per
+// key, no ballots, no atomics, no bank conflicts.  A lane sees at most 32 keys, so a byte never
+// overflows; the 128 columns are added up at the end two bytes at a time.
+//
+// Scatter: a tile is kTile consecutive entries; warp w owns a contiguous segment of it and walks it
+// in rounds of 32 (coalesced loads).  Stable rank of an entry = (entries with the same digit
 // earlier in the tile): inside a warp it comes from a ballot-built match mask against a
 // warp-private running counter in shared memory (plain load/store by the first lane of each digit
 // group - no shared-memory atomics, which cost 2 cycles per lane), across warps from one prefix
-// over the eight warp counters per digit.  Entries are then placed in shared memory in sorted order and
+// over the warp counters per digit.  Entries are then placed in shared memory in sorted order and
 // written out so that consecutive threads write consecutive addresses of a digit run.
-static constexpr int kRadixThreads = 256;
-static constexpr int kRadixWarps = kRadixThreads / 32;
-static constexpr int kRadixRounds = 16;
-static constexpr int kRadixTile = kRadixThreads * kRadixRounds;  // 4096 entries per CTA
+// Measured on 128 M uniform entries (profiles/r01_radix_sweep.txt): 256 threads x 16 rounds (24 warps per SM) 6.25 ms
+// per COO->CSR, 512 x 8 at two CTAs per SM 5.85, 512 x 8 squeezed into 40 registers for three CTAs (48 warps) 5.51;
+// 2048-entry tiles (256 x 8, 512 x 4) 6.25 / 6.08 - shorter digit runs cost what the extra warps give.
+static constexpr int kRadixThreads = 512;
+static constexpr int kRadixRounds = 8;       // 4096 entries per CTA, 64 KB of staging
+static constexpr int kRadixCtasPerSm = 3;
+static constexpr int kHistThreads = 128;
+
+template <int TILE>
+__global__ void __launch_bounds__(kHistThreads) radix_hist_kernel(int n, const int* __restrict__ key, int shift,
+                                                                  int* __restrict__ counts, int nblk)
+{
+    constexpr int kWarps = kHistThreads / 32;
+    constexpr int kPerLane = TILE / kHistThreads;
+    static_assert(kPerLane <= 255 && TILE % kHistThreads == 0, "a lane's byte counters must not overflow");
+    __shared__ unsigned cnt[kWarps][64][32];   // [warp][digit / 4][lane], byte (digit & 3)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 64; ++q) cnt[w][q][lane] = 0;   // own column: nobody else touches it before the barrier
+    const int base = blockIdx.x * TILE + w * (32 * kPerLane);
+    int kv[kPerLane];
+#pragma unroll
+    for (int r = 0; r < kPerLane; ++r) {
+        const int k = base + r * 32 + lane;
+        kv[r] = k < n ? ld_stream(key + k) : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kPerLane; ++r) {
+        if (kv[r] >= 0) {
+            const int d = (kv[r] >> shift) & 255;
+            cnt[w][d >> 2][lane] += 1u << ((d & 3) * 8);
+        }
+    }
+    __syncthreads();
+    // thread (q, h): word row q over lanes [16h, 16h+16) of every warp, rotated by q so that the 32
+    // threads of a warp read 32 different banks
+    const int q = threadIdx.x >> 1, h = threadIdx.x & 1;
+    unsigned even = 0, odd = 0;   // digits 4q (low half) and 4q+2 (high half) / digits 4q+1 and 4q+3
+#pragma unroll
+    for (int ww = 0; ww < kWarps; ++ww)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const unsigned v = cnt[ww][q][16 * h + ((j + q) & 15)];
+            even += v & 0x00ff00ffu;
+            odd += (v >> 8) & 0x00ff00ffu;
+        }
+    even += __shfl_xor_sync(0xffffffffu, even, 1);
+    odd += __shfl_xor_sync(0xffffffffu, odd, 1);
+    const int d0 = 4 * q + 2 * h;   // h = 0 stores digits 4q, 4q+1; h = 1 stores 4q+2, 4q+3
+    counts[(size_t)d0 * nblk + blockIdx.x] = h ? (int)(even >> 16) : (int)(even & 0xffffu);
+    counts[(size_t)(d0 + 1) * nblk + blockIdx.x] = h ? (int)(odd >> 16) : (int)(odd & 0xffffu);
+}
 
 // Lanes of the warp whose 8-bit digit equals this lane's, from eight ballots.  __match_any_sync
 // (SASS MATCH.ANY) gives the same mask in one instruction but retires only one warp per ~60
@@ -190,67 +244,42 @@ __device__ __forceinline__ unsigned match_digit(int d, bool ok)
     return ok ? m : 0u;
 }
 
-__global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(int n, const int* __restrict__ key, int shift,
-                                                                   int* __restrict__ counts, int nblk)
+template <int THREADS, int ROUNDS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) radix_scatter_kernel(int n, const int* __restrict__ key_in,
+                                                                const int* __restrict__ oth_in,
+                                                                const double* __restrict__ val_in, int shift,
+                                                                const int* __restrict__ offsets, int nblk,
+                                                                int* __restrict__ key_out, int* __restrict__ oth_out,
+                                                                double* __restrict__ val_out)
 {
-    __shared__ int wcnt[kRadixWarps][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < kRadixWarps; ++i) wcnt[i][threadIdx.x] = 0;
-    __syncthreads();
-    const int base = blockIdx.x * kRadixTile + w * (32 * kRadixRounds);
-    int kv[kRadixRounds];
-#pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        const int k = base + r * 32 + lane;
-        kv[r] = k < n ? ld_stream(key + k) : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        const bool ok = kv[r] >= 0;
-        const int d = (kv[r] >> shift) & 255;
-        const unsigned peers = match_digit(d, ok);
-        if (ok && (peers & ((1u << lane) - 1u)) == 0) wcnt[w][d] += __popc(peers);   // one lane per distinct digit
-        __syncwarp();
-    }
-    __syncthreads();
-    int tot = 0;
-#pragma unroll
-    for (int i = 0; i < kRadixWarps; ++i) tot += wcnt[i][threadIdx.x];
-    counts[threadIdx.x * nblk + blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, const int* __restrict__ key_in,
-                                                                      const int* __restrict__ oth_in,
-                                                                      const double* __restrict__ val_in, int shift,
-                                                                      const int* __restrict__ offsets, int nblk,
-                                                                      int* __restrict__ key_out, int* __restrict__ oth_out,
-                                                                      double* __restrict__ val_out)
-{
+    constexpr int kTile = THREADS * ROUNDS;
+    constexpr int kWarps = THREADS / 32;
+    static_assert(THREADS >= 256 && kTile <= 65535, "one thread per digit; 16-bit counters");
+    const int tile_id = blockIdx.x;
     extern __shared__ __align__(16) unsigned char radix_smem[];
-    double* s_val = reinterpret_cast<double*>(radix_smem);            // [kRadixTile]
-    int* s_key = reinterpret_cast<int*>(s_val + kRadixTile);          // [kRadixTile]
-    int* s_oth = s_key + kRadixTile;                                  // [kRadixTile]
-    __shared__ int wcnt[kRadixWarps][256];   // per-warp digit counters, later exclusive warp offsets
-    __shared__ int tile_off[256];            // first position of each digit inside the sorted tile
-    __shared__ int gbase[256];               // where this tile's run of each digit starts in the output
+    double* s_val = reinterpret_cast<double*>(radix_smem);            // [kTile]
+    int* s_key = reinterpret_cast<int*>(s_val + kTile);               // [kTile]
+    int* s_oth = s_key + kTile;                                       // [kTile]
+    __shared__ unsigned short wcnt[kWarps][256];   // per-warp digit counters, later exclusive warp offsets
+    __shared__ int tile_off[256];                  // first position of each digit inside the sorted tile
+    __shared__ int gbase[256];                     // where this tile's run of each digit starts in the output
+    __shared__ int dig_tot[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int tile = blockIdx.x * kRadixTile;
-    const int tile_n = min(kRadixTile, n - tile);
-#pragma unroll
-    for (int i = 0; i < kRadixWarps; ++i) wcnt[i][threadIdx.x] = 0;
-    gbase[threadIdx.x] = offsets[threadIdx.x * nblk + blockIdx.x];
+    const int tile = tile_id * kTile;
+    const int tile_n = min(kTile, n - tile);
+    for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&wcnt[0][0])[i] = 0;
+    if (threadIdx.x < 256) gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * nblk + tile_id];
     __syncthreads();
 
-    int kv[kRadixRounds], rk[kRadixRounds];  // key, rank inside the warp's segment (later: position in the tile)
+    int kv[ROUNDS], rk[ROUNDS];  // key, rank inside the warp's segment (later: position in the tile)
 #pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        const int e = w * (32 * kRadixRounds) + r * 32 + lane;   // position inside the tile
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = w * (32 * ROUNDS) + r * 32 + lane;   // position inside the tile
         kv[r] = e < tile_n ? ld_stream(key_in + tile + e) : 0;
     }
 #pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = w * (32 * ROUNDS) + r * 32 + lane;
         const bool ok = e < tile_n;
         const int d = (kv[r] >> shift) & 255;
         const unsigned peers = match_digit(d, ok);
@@ -258,30 +287,42 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
         int base = 0;
         if (ok) base = wcnt[w][d];
         __syncwarp();
-        if (ok && before == 0) wcnt[w][d] = base + __popc(peers);
+        if (ok && before == 0) wcnt[w][d] = (unsigned short)(base + __popc(peers));
         __syncwarp();
         rk[r] = base + before;
     }
     __syncthreads();
-    {   // thread d: exclusive prefix of digit d over the warps, and the digit's total in the tile
-        const int d = threadIdx.x;
+    {   // thread d < 256: exclusive prefix of digit d over the warps, then over the digits
+        const int d = threadIdx.x & 255;
         int run = 0;
+        if (threadIdx.x < 256) {
 #pragma unroll
-        for (int i = 0; i < kRadixWarps; ++i) {
-            const int c = wcnt[i][d];
-            wcnt[i][d] = run;
-            run += c;
+            for (int i = 0; i < kWarps; ++i) {
+                const int c = wcnt[i][d];
+                wcnt[i][d] = (unsigned short)run;
+                run += c;
+            }
         }
-        int tot;
-        const int excl = block_exclusive_scan(run, &tot);   // exclusive scan over digits
-        tile_off[d] = excl;
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (threadIdx.x < 256 && lane == 31) dig_tot[w] = inc;
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            int off = inc - run;
+            for (int i = 0; i < w; ++i) off += dig_tot[i];
+            tile_off[d] = off;
+        }
     }
     __syncthreads();
     // keys into their sorted slots; then the payload of each entry follows its key (loads issued
-    // only now: sixteen (index, value) pairs in flight per thread, no registers held across the ranking)
+    // only now: ROUNDS (index, value) pairs in flight per thread, no registers held across the ranking)
 #pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int e = w * (32 * ROUNDS) + r * 32 + lane;
         if (e < tile_n) {
             const int d = (kv[r] >> shift) & 255;
             rk[r] = tile_off[d] + wcnt[w][d] + rk[r];
@@ -289,21 +330,21 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
         }
     }
     {
-        int ov[kRadixRounds];
-        double vv[kRadixRounds];
+        int ov[ROUNDS];
+        double vv[ROUNDS];
 #pragma unroll
-        for (int r = 0; r < kRadixRounds; ++r) {
-            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = w * (32 * ROUNDS) + r * 32 + lane;
             ov[r] = e < tile_n ? ld_stream(oth_in + tile + e) : 0;
         }
 #pragma unroll
-        for (int r = 0; r < kRadixRounds; ++r) {
-            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = w * (32 * ROUNDS) + r * 32 + lane;
             vv[r] = e < tile_n ? ld_stream(val_in + tile + e) : 0.0;
         }
 #pragma unroll
-        for (int r = 0; r < kRadixRounds; ++r) {
-            const int e = w * (32 * kRadixRounds) + r * 32 + lane;
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int e = w * (32 * ROUNDS) + r * 32 + lane;
             if (e < tile_n) {
                 s_oth[rk[r]] = ov[r];
                 s_val[rk[r]] = vv[r];
@@ -311,7 +352,7 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tile_n; t += kRadixThreads) {
+    for (int t = threadIdx.x; t < tile_n; t += THREADS) {
         const int k = s_key[t];
         const int d = (k >> shift) & 255;
         const int out = gbase[d] + (t - tile_off[d]);
@@ -321,7 +362,42 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(int n, con
     }
 }
 
-static constexpr size_t kRadixSmem = (size_t)kRadixTile * (sizeof(double) + 2 * sizeof(int));   // 64 KB
+// Tried and dropped (profiles/r01_radix_sweep.txt): one persistent 1024-thread CTA per SM that receives the next
+// tile by TMA bulk copies while it ranks and writes the current one - bit-exact, but 5.66 ms against 5.42 per
+// COO->CSR on 128 M entries.  The pass is not waiting on DRAM (without its stores it still takes 1.0 of 1.3 ms):
+// it is the sum of ballot ranking (~70 instructions per 32 entries), bank conflicts of the random placement in
+// shared memory and the partly coalesced stores, and three independent CTAs per SM overlap those pipes better
+// than one CTA whose warps are all in the same phase.
+
+struct RadixArgs {
+    int n;
+    const int *kin, *oin;
+    const double* vin;
+    int shift;
+    int *counts, nblk, *ko, *oo;
+    double* vo;
+};
+
+template <int THREADS, int ROUNDS, int MINB>
+static int radix_pass(const RadixArgs& a, cudaStream_t s)
+{
+    constexpr int kTile = THREADS * ROUNDS;
+    constexpr size_t kSmem = (size_t)kTile * (sizeof(double) + 2 * sizeof(int));
+    static bool configured[16] = {};
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev & 15]) {
+        THSP_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<THREADS, ROUNDS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        configured[dev & 15] = true;
+    }
+    radix_hist_kernel<kTile><<<a.nblk, kHistThreads, 0, s>>>(a.n, a.kin, a.shift, a.counts, a.nblk);
+    THSP_LAUNCH_CHECK();
+    if (exclusive_scan(256 * a.nblk, a.counts, a.counts, s)) return 1;
+    radix_scatter_kernel<THREADS, ROUNDS, MINB><<<a.nblk, THREADS, kSmem, s>>>(a.n, a.kin, a.oin, a.vin, a.shift, a.counts, a.nblk, a.ko,
+                                                                              a.oo, a.vo);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
 
 // Sort the entries (key, oth, val) stably by key in [0, nbuckets).  The last pass writes the other
 // index and the value to (oth_final, val_final) when given - else they stay in scratch - and the
@@ -334,20 +410,13 @@ static int stable_sort_entries(int n, int nbuckets, const int* key, const int* o
     int bits = 1;
     while (bits < 31 && (1 << bits) < nbuckets) ++bits;
     const int passes = (bits + 7) / 8;
-    const int nblk = div_up(n, kRadixTile);
+    const int nblk = div_up(n, kRadixThreads * kRadixRounds);
     // two ping-pong sets of (val, key, oth); a set's value array comes first so it stays 16 B aligned
     const size_t np = ((size_t)n + 3) & ~(size_t)3;
     const size_t set_bytes = np * (sizeof(double) + 2 * sizeof(int));
     unsigned char* buf = static_cast<unsigned char*>(scratch(2 * set_bytes, 6));
     int* counts = static_cast<int*>(scratch(sizeof(int) * (256 * (size_t)nblk + 1), 7));
     if (!buf || !counts) return 1;
-    static bool configured[16] = {};
-    int dev = 0;
-    THSP_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev & 15]) {
-        THSP_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRadixSmem));
-        configured[dev & 15] = true;
-    }
     double* vbuf[2];
     int *kbuf[2], *obuf[2];
     for (int i = 0; i < 2; ++i) {
@@ -355,26 +424,21 @@ static int stable_sort_entries(int n, int nbuckets, const int* key, const int* o
         kbuf[i] = reinterpret_cast<int*>(vbuf[i] + np);
         obuf[i] = kbuf[i] + np;
     }
-    const int* kin = key;
-    const int* oin = oth;
-    const double* vin = val;
+    RadixArgs a{n, key, oth, val, 0, counts, nblk, nullptr, nullptr, nullptr};
     for (int p = 0; p < passes; ++p) {
         const bool last = p == passes - 1;
-        int* ko = kbuf[p & 1];
-        int* oo = (last && oth_final) ? oth_final : obuf[p & 1];
-        double* vo = (last && val_final) ? val_final : vbuf[p & 1];
-        radix_hist_kernel<<<nblk, kRadixThreads, 0, s>>>(n, kin, 8 * p, counts, nblk);
-        THSP_LAUNCH_CHECK();
-        if (exclusive_scan(256 * nblk, counts, counts, s)) return 1;
-        radix_scatter_kernel<<<nblk, kRadixThreads, kRadixSmem, s>>>(n, kin, oin, vin, 8 * p, counts, nblk, ko, oo, vo);
-        THSP_LAUNCH_CHECK();
-        kin = ko;
-        oin = oo;
-        vin = vo;
+        a.shift = 8 * p;
+        a.ko = kbuf[p & 1];
+        a.oo = (last && oth_final) ? oth_final : obuf[p & 1];
+        a.vo = (last && val_final) ? val_final : vbuf[p & 1];
+        if (radix_pass<kRadixThreads, kRadixRounds, kRadixCtasPerSm>(a, s)) return 1;
+        a.kin = a.ko;
+        a.oin = a.oo;
+        a.vin = a.vo;
     }
-    *sorted_key = kin;
-    *sorted_oth = oin;
-    *sorted_val = vin;
+    *sorted_key = a.kin;
+    *sorted_oth = a.oin;
+    *sorted_val = a.vin;
     return 0;
 }
 
@@ -392,35 +456,40 @@ __global__ void __launch_bounds__(256) sorted_check_kernel(int n, const int* __r
 // empty rows) are queued in shared memory and filled by the whole CTA with coalesced stores; all
 // gaps together are nbuckets stores.  No atomics - the earlier atomic histogram serialised on
 // hub rows (3.7 ms on the R-MAT matrix).
-static constexpr int kBndItems = 4;
+static constexpr int kBndItems = 8;
 __global__ void __launch_bounds__(256) boundaries_kernel(int n, int nbuckets, const int* __restrict__ key, int* __restrict__ ptr)
 {
     __shared__ int q_lo[256 * kBndItems], q_hi[256 * kBndItems], q_pos[256 * kBndItems];
     __shared__ int q_n;
     if (threadIdx.x == 0) q_n = 0;
     __syncthreads();
-    // positions p0 .. p0+3 of this thread; position n (one past the end) closes the last buckets
+    // positions p0 .. p0+7 of this thread; position n (one past the end) closes the last buckets
     const int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kBndItems;
     if (p0 <= n) {
         int k[kBndItems + 1];   // k[0] = key[p0-1], k[1+j] = key[p0+j]
         k[0] = p0 == 0 ? -1 : ld_stream(key + p0 - 1);
         if (p0 + kBndItems <= n && (((uintptr_t)key) & 15) == 0) {
-            const int4 v = ld_stream4(key + p0);
-            k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+#pragma unroll
+            for (int j = 0; j < kBndItems; j += 4) {
+                const int4 v = ld_stream4(key + p0 + j);
+                k[1 + j] = v.x; k[2 + j] = v.y; k[3 + j] = v.z; k[4 + j] = v.w;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < kBndItems; ++j) k[1 + j] = p0 + j < n ? ld_stream(key + p0 + j) : nbuckets;
         }
+        if (k[0] != k[kBndItems]) {   // keys do not decrease: equal ends = one bucket throughout, nothing starts here
 #pragma unroll
-        for (int j = 0; j < kBndItems; ++j) {
-            const int64_t p = p0 + j;
-            if (p > n) break;
-            const int lo = max(k[j] + 1, 0), hi = min(k[1 + j], nbuckets);   // fill ptr[lo..hi] with p
-            if (hi - lo >= 8) {
-                const int q = atomicAdd(&q_n, 1);
-                q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = (int)p;
-            } else {
-                for (int r = lo; r <= hi; ++r) ptr[r] = (int)p;
+            for (int j = 0; j < kBndItems; ++j) {
+                const int64_t p = p0 + j;
+                if (p > n) break;
+                const int lo = max(k[j] + 1, 0), hi = min(k[1 + j], nbuckets);   // fill ptr[lo..hi] with p
+                if (hi - lo >= 8) {
+                    const int q = atomicAdd(&q_n, 1);
+                    q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = (int)p;
+                } else {
+                    for (int r = lo; r <= hi; ++r) ptr[r] = (int)p;
+                }
             }
         }
     }
@@ -435,10 +504,19 @@ static int keys_unsorted(int n, const int* key, int* unsorted_host, cudaStream_t
     int* flag = static_cast<int*>(scratch(sizeof(int), 1));
     if (!flag) return 1;
     THSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-    sorted_check_kernel<<<std::min(div_up(n, 256), sm_count() * 32), 256, 0, s>>>(n, key, flag);
-    THSP_LAUNCH_CHECK();
-    THSP_CUDA(cudaMemcpyAsync(unsorted_host, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    THSP_CUDA(cudaStreamSynchronize(s));
+    // unsorted input shows in the first stretch: look at 1 M keys before reading all of them
+    const int probe = 1 << 20;
+    int done = 0;
+    for (int part = 0; part < 2 && done < n; ++part) {
+        const int upto = part == 0 ? std::min(n, probe) : n;
+        const int first = done > 0 ? done - 1 : 0;   // the pair across the seam belongs to the second part
+        sorted_check_kernel<<<std::min(div_up(upto - first, 256), sm_count() * 32), 256, 0, s>>>(upto - first, key + first, flag);
+        THSP_LAUNCH_CHECK();
+        THSP_CUDA(cudaMemcpyAsync(unsorted_host, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        THSP_CUDA(cudaStreamSynchronize(s));
+        if (*unsorted_host) break;
+        done = upto;
+    }
     return 0;
 }
 
@@ -518,6 +596,7 @@ __global__ void __launch_bounds__(kScanThreads) diag_scatter_kernel(int n, const
                                                                     int cap, double* __restrict__ diag)
 {
     __shared__ int tot;
+    if (boff[blockIdx.x + 1] == boff[blockIdx.x]) return;   // no diagonal entry in this tile: nothing to read again
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
     bool f[kScanItems];
     diag_flags(n, base, ri, ci, f);
