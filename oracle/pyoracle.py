@@ -306,3 +306,25 @@ class Ref(_Base):
         dt = float(self.fn("time_power_iteration", C.c_double)(C.c_int(n), _vp(rp), _vp(ci), _vp(v), _vp(x), _vp(y),
                                                                 C.c_int(steps), C.byref(nrm)))
         return dt, nrm.value, x
+
+
+class RefO3(Ref):
+    """The same reference sources built with -O3 -march=x86-64-v3 (oracle/Makefile): a timing baseline only -
+    FMA contraction changes last bits, so parity is never checked against it."""
+    path = os.path.join(_HERE, "_ref", "libref_o3.so")
+    FLAGS = "-O3 -march=x86-64-v3 -fopenmp -DUSE_OPENMP"
+
+    @staticmethod
+    def runnable():
+        """The host CPU has what x86-64-v3 code needs (the library was built on another machine)."""
+        if not os.path.exists(RefO3.path):
+            return False
+        try:
+            flags = set()
+            for ln in open("/proc/cpuinfo"):
+                if ln.startswith("flags"):
+                    flags = set(ln.split(":", 1)[1].split())
+                    break
+            return {"avx2", "fma", "bmi2", "f16c", "movbe"} <= flags
+        except OSError:
+            return False

@@ -107,6 +107,28 @@ def test_oracle_matches_live_reference(oracle, ref, seed):
     for u, w in zip(da, db): eq(u, w)
 
 
+def test_rebuilt_o3_reference_is_a_timing_baseline_only(oracle):
+    """oracle/_ref/libref_o3.so (the reference at -O3 -march=x86-64-v3, timed beside the stock build by bench.py) loads
+    next to libref.so and computes the same SpMV up to FMA contraction: index work identical, values within 1e-12."""
+    import pyoracle
+    if not pyoracle.RefO3.runnable():
+        pytest.skip("libref_o3.so not built or this CPU lacks AVX2/FMA")
+    r3 = pyoracle.RefO3(); r3.set_threads(2)
+    rs = np.random.RandomState(7)
+    nrow, ncol, nnz = 300, 280, 4000
+    ri = rs.randint(0, nrow, nnz).astype(np.int32); ci = rs.randint(0, ncol, nnz).astype(np.int32)
+    keep = ~((ri == ci) | ((ri == 0) & (ci == ncol - 1)))
+    ri, ci = ri[keep], ci[keep]
+    va = rs.uniform(-1, 1, len(ri)); x = rs.uniform(0, 1, ncol); y0 = rs.uniform(-1, 1, nrow)
+    a = oracle.coo2csr(nrow, ncol, ri, ci, va); b = r3.coo2csr(nrow, ncol, ri, ci, va)
+    for u, w in zip(a[:3], b[:3]): eq(u, w)
+    rp, co, cv, _ = a
+    y, y3 = oracle.csr_spmv(nrow, ncol, rp, co, cv, x, y0), r3.csr_spmv(nrow, ncol, rp, co, cv, x, y0)
+    scale = np.abs(y0) + np.bincount(ri, np.abs(va * x[ci]), nrow)
+    assert np.max(np.abs(y - y3) / np.maximum(scale, 1e-300)) <= 1e-12
+    assert r3.time_csr_spmv(nrow, ncol, rp, co, cv, x, 2) > 0
+
+
 def test_generators_are_consistent(oracle):
     """The synthetic matrices the benches use: structure checks on the CPU twins."""
     rp, ci, va = oracle.gen_stencil27_csr(5)
