@@ -24,6 +24,7 @@
 //
 // The plan picks kernel and L from the row-length histogram (thsp_csr_plan_create).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -616,9 +617,19 @@ using namespace thsp;
 struct HostPipe {
     int nchunks = 0;
     std::vector<int> row0, cmin, cmax;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t begin = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_cap = nullptr;
+    cudaEvent_t begin = nullptr, out_done = nullptr;
     std::vector<cudaEvent_t> in_done, k_done;
+    // The whole call as a CUDA graph, captured the second time the same four buffers come in: the ~4 copies, kernel
+    // and 4 event calls per chunk cost the submitting thread ~30 us, more than a chunk's transfer once chunks are
+    // small enough to keep y close behind x on the link (profiles/r01_e2e_chunks.txt).
+    cudaGraphExec_t exec = nullptr;
+    const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int key_acc = -1, key_seen = 0;
+    unsigned kernels_per_call = 0;
+    // THSP_HOST_TRACE=1: timing events per chunk (x piece in, kernel start / end, y piece out), printed after the call
+    cudaEvent_t t_begin = nullptr;
+    std::vector<cudaEvent_t> t_in, t_k0, t_k1, t_out;
 };
 
 struct thsp_csr_plan {
@@ -781,6 +792,9 @@ int thsp_csr_plan_destroy(thsp_csr_plan* plan)
         for (auto e : hp->in_done) cudaEventDestroy(e);
         for (auto e : hp->k_done) cudaEventDestroy(e);
         if (hp->begin) cudaEventDestroy(hp->begin);
+        if (hp->out_done) cudaEventDestroy(hp->out_done);
+        if (hp->exec) cudaGraphExecDestroy(hp->exec);
+        if (hp->s_cap) cudaStreamDestroy(hp->s_cap);
         if (hp->s_in) cudaStreamDestroy(hp->s_in);
         if (hp->s_out) cudaStreamDestroy(hp->s_out);
         delete hp;
@@ -937,7 +951,9 @@ static int build_host_pipe(thsp_csr_plan* p, cudaStream_t s)
     THSP_CUDA(cudaStreamSynchronize(s));
     THSP_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
     THSP_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+    THSP_CUDA(cudaStreamCreateWithFlags(&hp->s_cap, cudaStreamNonBlocking));
     THSP_CUDA(cudaEventCreateWithFlags(&hp->begin, cudaEventDisableTiming));
+    THSP_CUDA(cudaEventCreateWithFlags(&hp->out_done, cudaEventDisableTiming));
     hp->in_done.resize(n);
     hp->k_done.resize(n);
     for (int c = 0; c < n; ++c) {
@@ -949,19 +965,18 @@ static int build_host_pipe(thsp_csr_plan* p, cudaStream_t s)
 }
 
 // Host x in, host y out.  Three streams: x pieces arrive on s_in in the order the row chunks need
-// them, each chunk is multiplied on the caller's stream as soon as its column range is there, its
-// rows of y leave on s_out while the next chunk runs.  PCIe is full duplex, so for banded
-// matrices the call costs about one transfer of x plus one chunk, not x + SpMV + y in sequence.
-int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host, double* y_host, double* x_dev,
-                                double* y_dev, int accumulate, thsp_stream_t stream)
+// them, each chunk is multiplied on `s` as soon as its column range is there, its rows of y leave
+// on s_out while the next chunk runs; s_out joins `s` at the end.  PCIe is full duplex, so for
+// banded matrices the call costs about one transfer of x plus one chunk, not x + SpMV + y in sequence.
+static int host_pipe_enqueue(thsp_csr_plan* plan, const double* x_host, double* y_host, double* x_dev, double* y_dev,
+                             int accumulate, cudaStream_t s)
 {
-    THSP_REQUIRE(cplan != nullptr && cplan->value_bytes == 8, "plan is null or not fp64");
-    thsp_csr_plan* plan = const_cast<thsp_csr_plan*>(cplan);
-    cudaStream_t s = as_stream(stream);
-    if (plan->nrow <= 0) return 0;
-    if (!plan->pipe && build_host_pipe(plan, s)) return 1;
     HostPipe* hp = plan->pipe;
     const double* val = static_cast<const double*>(plan->val);
+    static const int env_ctas = getenv("THSP_HOST_CTAS") ? atoi(getenv("THSP_HOST_CTAS")) : 0;
+    const int ctas = env_ctas > 0 ? env_ctas : plan->ctas;
+    const bool trace = !hp->t_in.empty();
+    if (trace) THSP_CUDA(cudaEventRecord(hp->t_begin, s));
     THSP_CUDA(cudaEventRecord(hp->begin, s));          // earlier work on the scratch buffers
     THSP_CUDA(cudaStreamWaitEvent(hp->s_in, hp->begin, 0));
     THSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->begin, 0));
@@ -989,22 +1004,103 @@ int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host
         if (accumulate)
             THSP_CUDA(cudaMemcpyAsync(y_dev + r0, y_host + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyHostToDevice, hp->s_in));
         THSP_CUDA(cudaEventRecord(hp->in_done[c], hp->s_in));
+        if (trace) THSP_CUDA(cudaEventRecord(hp->t_in[c], hp->s_in));
         THSP_CUDA(cudaStreamWaitEvent(s, hp->in_done[c], 0));
+        if (trace) THSP_CUDA(cudaEventRecord(hp->t_k0[c], s));
         int rc;
         if (hp->nchunks == 1) rc = plan_spmv<double>(plan, x_dev, y_dev, accumulate, s);
         else if (plan->kernel == THSP_CSR_STREAM)
-            rc = run_stream<double>(plan->stream_cfg, plan->ctas, r1 - r0, plan->nnz, plan->row_ptr + r0, plan->col_ind, val, x_dev,
+            rc = run_stream<double>(plan->stream_cfg, ctas, r1 - r0, plan->nnz, plan->row_ptr + r0, plan->col_ind, val, x_dev,
                                     y_dev + r0, accumulate, s);
         else
             rc = run_vector<double>(plan->kernel == THSP_CSR_SCALAR ? 1 : plan->lanes, r1 - r0, plan->row_ptr + r0, plan->col_ind, val,
                                     x_dev, y_dev + r0, accumulate, s);
         if (rc) return rc;
         THSP_CUDA(cudaEventRecord(hp->k_done[c], s));
+        if (trace) THSP_CUDA(cudaEventRecord(hp->t_k1[c], s));
         THSP_CUDA(cudaStreamWaitEvent(hp->s_out, hp->k_done[c], 0));
         THSP_CUDA(cudaMemcpyAsync(y_host + r0, y_dev + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, hp->s_out));
+        if (trace) THSP_CUDA(cudaEventRecord(hp->t_out[c], hp->s_out));
     }
-    THSP_CUDA(cudaStreamSynchronize(hp->s_out));
+    THSP_CUDA(cudaEventRecord(hp->out_done, hp->s_out));
+    THSP_CUDA(cudaStreamWaitEvent(s, hp->out_done, 0));
+    return 0;
+}
+
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host, double* y_host, double* x_dev,
+                                double* y_dev, int accumulate, thsp_stream_t stream)
+{
+    THSP_REQUIRE(cplan != nullptr && cplan->value_bytes == 8, "plan is null or not fp64");
+    thsp_csr_plan* plan = const_cast<thsp_csr_plan*>(cplan);
+    cudaStream_t s = as_stream(stream);
+    if (plan->nrow <= 0) return 0;
+    if (!plan->pipe && build_host_pipe(plan, s)) return 1;
+    HostPipe* hp = plan->pipe;
+    static const int env_trace = getenv("THSP_HOST_TRACE") ? atoi(getenv("THSP_HOST_TRACE")) : 0;
+    static const int no_graph = env_trace || (getenv("THSP_HOST_NOGRAPH") ? atoi(getenv("THSP_HOST_NOGRAPH")) : 0);
+    if (env_trace && hp->t_in.empty()) {
+        THSP_CUDA(cudaEventCreate(&hp->t_begin));
+        for (auto* v : {&hp->t_in, &hp->t_k0, &hp->t_k1, &hp->t_out}) {
+            v->resize(hp->nchunks);
+            for (auto& e : *v) THSP_CUDA(cudaEventCreate(&e));
+        }
+    }
+    const void* key[4] = {x_host, y_host, x_dev, y_dev};
+    const bool same = memcmp(key, hp->key, sizeof(key)) == 0 && hp->key_acc == accumulate;
+    if (!same) {
+        if (hp->exec) {
+            cudaGraphExecDestroy(hp->exec);
+            hp->exec = nullptr;
+        }
+        memcpy(hp->key, key, sizeof(key));
+        hp->key_acc = accumulate;
+        hp->key_seen = 0;
+    }
+    ++hp->key_seen;
+    if (!hp->exec && hp->key_seen >= 2 && hp->nchunks > 1 && !no_graph && is_pinned_host(x_host) && is_pinned_host(y_host)) {
+        // second call with the same buffers (the first one ran eagerly and sized every scratch buffer and attribute)
+        const uint64_t before = thsp_launch_count();
+        cudaGraph_t g = nullptr;
+        THSP_CUDA(cudaStreamBeginCapture(hp->s_cap, cudaStreamCaptureModeRelaxed));
+        const int rc = host_pipe_enqueue(plan, x_host, y_host, x_dev, y_dev, accumulate, hp->s_cap);
+        const cudaError_t e = cudaStreamEndCapture(hp->s_cap, &g);
+        hp->kernels_per_call = (unsigned)(thsp_launch_count() - before);
+        note_launch(0u - hp->kernels_per_call);   // captured, not launched
+        if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&hp->exec, g, 0) != cudaSuccess) hp->exec = nullptr;
+        if (g) cudaGraphDestroy(g);
+        if (rc != 0 || e != cudaSuccess) {
+            cudaGetLastError();
+            hp->exec = nullptr;   // fall back to eager submission below
+        }
+    }
+    if (hp->exec) {
+        THSP_CUDA(cudaGraphLaunch(hp->exec, s));
+        note_launch(hp->kernels_per_call);
+    } else if (host_pipe_enqueue(plan, x_host, y_host, x_dev, y_dev, accumulate, s)) {
+        return 1;
+    }
     THSP_CUDA(cudaStreamSynchronize(s));
+    if (env_trace && hp->key_seen == 4) {   // one warmed-up call, chunk by chunk (ms since the call began)
+        fprintf(stderr, "thsp host pipe: chunk rows | x in | kernel start end | y out\n");
+        for (int c = 0; c < hp->nchunks; ++c) {
+            float a = 0, b = 0, d = 0, e = 0;
+            cudaEventElapsedTime(&a, hp->t_begin, hp->t_in[c]);
+            cudaEventElapsedTime(&b, hp->t_begin, hp->t_k0[c]);
+            cudaEventElapsedTime(&d, hp->t_begin, hp->t_k1[c]);
+            cudaEventElapsedTime(&e, hp->t_begin, hp->t_out[c]);
+            fprintf(stderr, "  %2d %8d | %6.3f | %6.3f %6.3f | %6.3f\n", c, hp->row0[c + 1] - hp->row0[c], a, b, d, e);
+        }
+    }
     return 0;
 }
 

@@ -270,7 +270,13 @@ def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
     xd = torch.full((ncol,), float("nan"), dtype=torch.float64, device="cuda")
     yd = torch.full((nrow,), float("nan"), dtype=torch.float64, device="cuda")
     lib = thsp.load()
-    for _ in range(2):   # twice: the second call reuses the pipeline built by the first
+    yh_first = yh
+    yh_other = torch.from_numpy(y0.copy()).pin_memory()
+    y_pageable = y0.copy()
+    # call 1 runs eagerly and builds the pipeline, call 2 captures it as a CUDA graph, calls 3-4 replay the graph,
+    # call 5 brings another pinned y (graph dropped, eager again), call 6 a pageable y (never captured)
+    for it in range(6):
+        yh = yh_first if it < 4 else (yh_other if it == 4 else torch.from_numpy(y_pageable))
         yh.copy_(torch.from_numpy(y0))
         thsp.lib.check(lib.thsp_csr_plan_spmv_host_f64(A.plan(), ctypes.c_void_p(xh.data_ptr()), ctypes.c_void_p(yh.data_ptr()),
                                                        thsp.lib.ptr(xd), thsp.lib.ptr(yd), 1 if accumulate else 0, thsp.lib.current_stream()))
