@@ -47,6 +47,7 @@ int ensure_device();       // 0 if a CUDA device is usable, else sets error
 // Per-device scratch that lives for the process (partials of reductions, scan block sums...).
 // Grows monotonically; never shared between streams concurrently by this library's own calls.
 void* scratch(size_t bytes, int slot);
+uint64_t scratch_uses(int slot);   // how often the slot has been handed out on the current device
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

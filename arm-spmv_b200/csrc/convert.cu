@@ -557,6 +557,16 @@ __global__ void __launch_bounds__(256) ell_write_kernel(int nrow, int width, con
     }
 }
 
+// longest row from the row pointers
+__global__ void __launch_bounds__(256) max_diff_kernel(int nrow, const int* __restrict__ ptr, int* __restrict__ out)
+{
+    int m = 0;
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < nrow; r += gridDim.x * 256) m = max(m, ptr[r + 1] - ptr[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 __global__ void __launch_bounds__(256) max_len_kernel(int nrow, const int* __restrict__ cnt, int* __restrict__ out)
 {
     int m = 0;
@@ -745,25 +755,90 @@ int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_s
     return 0;
 }
 
+// Row-sorted entries + row pointers of a COO matrix in scratch (slot 2: pointers, slot 6: sorted copies when the input
+// is not sorted already).
+static int ell_sorted_rows(int nrow, int nnz, const int* row_ind, const int* col_ind, const double* val, int** rp_out,
+                           const int** sc, const double** sv, cudaStream_t s)
+{
+    int* rp = static_cast<int*>(scratch(sizeof(int) * ((size_t)nrow + 2), 2));
+    if (!rp) return 1;
+    *rp_out = rp;
+    *sc = col_ind;
+    *sv = val;
+    if (nnz <= 0) {
+        THSP_CUDA(cudaMemsetAsync(rp, 0, sizeof(int) * ((size_t)nrow + 1), s));
+        return 0;
+    }
+    int unsorted = 0;
+    if (keys_unsorted(nnz, row_ind, &unsorted, s)) return 1;
+    const int* sk = row_ind;
+    if (unsorted && stable_sort_entries(nnz, nrow, row_ind, col_ind, val, nullptr, nullptr, &sk, sc, sv, s)) return 1;
+    return bucket_pointers(nrow, nnz, sk, rp, s);
+}
+
+// What thsp_coo2ell_prepare left in scratch for the thsp_coo2ell that follows it.
+struct EllPrepared {
+    bool valid = false;
+    int dev = -1, nrow = 0, nnz = 0, width = 0;
+    const int *ri = nullptr, *ci = nullptr;
+    const double* va = nullptr;
+    const int *rp = nullptr, *sc = nullptr;
+    const double* sv = nullptr;
+    uint64_t uses2 = 0, uses6 = 0;
+};
+static EllPrepared g_ell_prepared;
+
+int thsp_coo2ell_prepare(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val, int* width,
+                         thsp_stream_t stream)
+{
+    (void)ncol;
+    if (ensure_device()) return 1;
+    cudaStream_t s = as_stream(stream);
+    g_ell_prepared.valid = false;
+    *width = 0;
+    if (nrow <= 0 || nnz <= 0) return 0;
+    int* rp = nullptr;
+    const int* sc = nullptr;
+    const double* sv = nullptr;
+    if (ell_sorted_rows(nrow, nnz, row_ind, col_ind, val, &rp, &sc, &sv, s)) return 1;
+    int* mx = rp + nrow + 1;
+    THSP_CUDA(cudaMemsetAsync(mx, 0, sizeof(int), s));
+    max_diff_kernel<<<std::min(div_up(nrow, 256), sm_count() * 8), 256, 0, s>>>(nrow, rp, mx);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaMemcpyAsync(width, mx, sizeof(int), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    EllPrepared& e = g_ell_prepared;
+    THSP_CUDA(cudaGetDevice(&e.dev));
+    e.nrow = nrow; e.nnz = nnz; e.width = *width;
+    e.ri = row_ind; e.ci = col_ind; e.va = val;
+    e.rp = rp; e.sc = sc; e.sv = sv;
+    e.uses2 = scratch_uses(2);
+    e.uses6 = scratch_uses(6);
+    e.valid = true;
+    return 0;
+}
+
 int thsp_coo2ell(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val, int width,
                  int* out_col_ind, double* out_val, double* diagonal, int* ndiag, thsp_stream_t stream)
 {
     (void)ncol;
     if (ensure_device()) return 1;
     cudaStream_t s = as_stream(stream);
+    EllPrepared prep = g_ell_prepared;   // good for one call
+    g_ell_prepared.valid = false;
     if (nrow > 0 && width > 0) {
-        int* rp = static_cast<int*>(scratch(sizeof(int) * ((size_t)nrow + 2), 2));
-        if (!rp) return 1;
-        const int* sc = col_ind;
-        const double* sv = val;
-        if (nnz <= 0) {
-            THSP_CUDA(cudaMemsetAsync(rp, 0, sizeof(int) * ((size_t)nrow + 1), s));
-        } else {
-            int unsorted = 0;
-            if (keys_unsorted(nnz, row_ind, &unsorted, s)) return 1;
-            const int* sk = row_ind;
-            if (unsorted && stable_sort_entries(nnz, nrow, row_ind, col_ind, val, nullptr, nullptr, &sk, &sc, &sv, s)) return 1;
-            if (bucket_pointers(nrow, nnz, sk, rp, s)) return 1;
+        int dev = -1;
+        THSP_CUDA(cudaGetDevice(&dev));
+        const bool reuse = prep.valid && prep.dev == dev && prep.nrow == nrow && prep.nnz == nnz && prep.width == width &&
+                           prep.ri == row_ind && prep.ci == col_ind && prep.va == val && prep.uses2 == scratch_uses(2) &&
+                           prep.uses6 == scratch_uses(6);
+        const int* rp = prep.rp;
+        const int* sc = prep.sc;
+        const double* sv = prep.sv;
+        if (!reuse) {
+            int* rp_new = nullptr;
+            if (ell_sorted_rows(nrow, nnz, row_ind, col_ind, val, &rp_new, &sc, &sv, s)) return 1;
+            rp = rp_new;
         }
         ell_write_kernel<<<div_up(nrow, 256), 256, 0, s>>>(nrow, width, rp, sc, sv, out_col_ind, out_val);
         THSP_LAUNCH_CHECK();

@@ -52,7 +52,7 @@ void ell_from_coo(ELLMatrix& D, const COOMatrix& A)
     D.nnz = A.nnz;
     CooArrays in(A);
     int width = 0;
-    ok(thsp_coo2ell_width(A.nrow, A.nnz, in.ri, &width, nullptr), "ELL width");
+    ok(thsp_coo2ell_prepare(A.nrow, A.ncol, A.nnz, in.ri, in.ci, in.va, &width, nullptr), "ELL width");
     D.nonzeros_in_row = width;
     const size_t total = (size_t)A.nrow * (size_t)width;
     D.col_ind = alloc<int>(total);

@@ -53,6 +53,7 @@ static constexpr int kSlots = 8;
 struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
+    uint64_t uses = 0;   // handed out this many times: lets a two-step call notice that somebody used the slot in between
 };
 static Scratch g_scratch[kMaxDev][kSlots];
 static std::mutex g_scratch_mu;
@@ -63,6 +64,7 @@ void* scratch(size_t bytes, int slot)
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev || slot < 0 || slot >= kSlots) return nullptr;
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     Scratch& s = g_scratch[dev][slot];
+    ++s.uses;
     if (s.cap < bytes) {
         if (s.p) {
             cudaDeviceSynchronize();
@@ -78,6 +80,14 @@ void* scratch(size_t bytes, int slot)
         s.cap = cap;
     }
     return s.p;
+}
+
+uint64_t scratch_uses(int slot)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev || slot < 0 || slot >= kSlots) return 0;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    return g_scratch[dev][slot].uses;
 }
 
 }  // namespace thsp

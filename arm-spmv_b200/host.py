@@ -194,7 +194,8 @@ class ELLMatrix:
             dev = A.values.device
             self.nrow, self.ncol, self.nnz = A.nrow, A.ncol, A.nnz
             k = C.c_int(0)
-            check(load().thsp_coo2ell_width(A.nrow, A.nnz, ptr(A.row_ind), C.byref(k), current_stream()))
+            check(load().thsp_coo2ell_prepare(A.nrow, A.ncol, A.nnz, ptr(A.row_ind), ptr(A.col_ind), ptr(A.values), C.byref(k),
+                                              current_stream()))
             self.nonzeros_in_row = k.value
             self.col_ind = torch.empty(A.nrow * k.value, dtype=I32, device=dev)
             self.values = torch.empty(A.nrow * k.value, dtype=F64, device=dev)

@@ -157,6 +157,13 @@ THSP_API int thsp_coo2csc(int nrow, int ncol, int nnz, const int* row_ind, const
 /* ELLMatrix::ELLMatrix(const COOMatrix&) (src/matrix.cpp:450-500) in two steps because the
  * caller must allocate nrow*width slots: width = longest row, then the fill. Synchronous. */
 THSP_API int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_stream_t stream);
+/* The same width, obtained by doing the expensive half of the conversion (the row sort) and keeping it in the
+ * library's scratch: a thsp_coo2ell with the same arrays, sizes and width that FOLLOWS it on this device - no other
+ * conversion, Matrix Market parse or merge-path SpMV in between, entries unchanged - only writes the slab (one pass
+ * over the entries instead of a histogram plus the whole conversion).  Anything else in between is detected and
+ * thsp_coo2ell converts from scratch as usual.  Synchronous; not re-entrant (like the reference). */
+THSP_API int thsp_coo2ell_prepare(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                                  int* width, thsp_stream_t stream);
 THSP_API int thsp_coo2ell(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
                           int width, int* out_col_ind, double* out_val, double* diagonal, int* ndiag,
                           thsp_stream_t stream);

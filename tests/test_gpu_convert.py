@@ -140,6 +140,41 @@ def test_exclusive_scan(thsp, cuda, n):
     assert_bits(host(d), want, f"scan in place {n}")
 
 
+@pytest.mark.parametrize("between", ["nothing", "other_conversion", "merge_spmv", "other_width", "other_arrays", "no_prepare"])
+def test_ell_two_step_conversion(thsp, cuda, oracle, between):
+    """thsp_coo2ell_prepare keeps the row sort in the library's scratch for the thsp_coo2ell that follows; whatever
+    happens in between (another conversion, a kernel that borrows the same scratch, different arguments, no prepare at
+    all) the slab must equal the reference constructor's (src/matrix.cpp:450-500) bit for bit."""
+    from arm_spmv_b200 import host as H
+    lib = thsp.load(); chk = thsp.lib.check; ptr = thsp.lib.ptr; cs = thsp.lib.current_stream
+    rs = np.random.RandomState(5)
+    nrow, ncol, nnz = 20000, 15000, 150000
+    ri = rs.randint(0, nrow, nnz).astype(np.int32); ci = rs.randint(0, ncol, nnz).astype(np.int32); va = rs.uniform(-1, 1, nnz)
+    k, eco, eva, _ = oracle.coo2ell(nrow, ncol, ri, ci, va)
+    A = H.COOMatrix(nrow, ncol, ri, ci, va)
+    w = ctypes.c_int(0)
+    if between != "no_prepare":
+        chk(lib.thsp_coo2ell_prepare(nrow, ncol, nnz, ptr(A.row_ind), ptr(A.col_ind), ptr(A.values), ctypes.byref(w), cs()))
+        assert w.value == k
+    src = A
+    if between == "other_conversion":      # overwrites the sorted entries and the row pointers in scratch
+        B = H.COOMatrix(nrow, ncol, ci % nrow, ri % ncol, -va)
+        H.CSRMatrix(B); H.ELLMatrix(B)
+    elif between == "merge_spmv":          # the merge-path kernel's carries live in the row-pointer slot
+        R = H.CSRMatrix(H.rmat_coo(12, 40000, 3))
+        x = H.gen_vector(R.ncol, 1); y = H.Vector(R.nrow); y.Fill(0.0)
+        H.csr_spmv_kernel(4, 1, R, x.values, y.values, True)
+    elif between == "other_arrays":        # same contents at other addresses: nothing to reuse
+        src = H.COOMatrix(nrow, ncol, ri.copy(), ci.copy(), va.copy())
+    width = k + 3 if between == "other_width" else k
+    oc = torch.full((nrow * width,), -7, dtype=torch.int32, device="cuda")
+    ov = torch.full((nrow * width,), float("nan"), dtype=torch.float64, device="cuda")
+    chk(lib.thsp_coo2ell(nrow, ncol, nnz, ptr(src.row_ind), ptr(src.col_ind), ptr(src.values), width, ptr(oc), ptr(ov), None, None, cs()))
+    if between == "other_width":   # a wider slab = the same slots followed by padding columns (col 0, +0.0)
+        eco = np.concatenate([eco, np.zeros(3 * nrow, np.int32)]); eva = np.concatenate([eva, np.zeros(3 * nrow)])
+    assert_bits(host(oc), eco, f"ell col ({between})"); assert_bits(host(ov), eva, f"ell val ({between})")
+
+
 def test_generators_match_cpu_twins(thsp, cuda, oracle):
     from arm_spmv_b200 import host as H
     A = H.stencil27_csr(9)
