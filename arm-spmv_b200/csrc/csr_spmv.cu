@@ -504,12 +504,25 @@ __global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry
     int k = i - 1;
     while (k >= 0 && carry_row[k] < 0) --k;
     if (k >= 0 && carry_row[k] == r) return;  // not the first slot of this row
+    // A hub row of a power-law matrix crosses hundreds of runs: fetch eight slots at a time so that the chain
+    // costs one memory round trip per eight partials instead of one each; the additions stay left to right.
     V acc = y[r];
-    for (int j = i; j < nslots; ++j) {
-        const int rj = carry_row[j];
-        if (rj < 0) continue;
-        if (rj != r) break;
-        acc = add_rn(acc, carry_val[j]);
+    bool open = true;
+    for (int j0 = i; open && j0 < nslots; j0 += 8) {
+        int rj[8];
+        V vj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = min(j0 + u, nslots - 1);
+            rj[u] = carry_row[j];
+            vj[u] = carry_val[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (!open || j0 + u >= nslots || rj[u] < 0) continue;
+            if (rj[u] != r) open = false;
+            else acc = add_rn(acc, vj[u]);
+        }
     }
     y[r] = acc;
 }

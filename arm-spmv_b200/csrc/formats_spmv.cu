@@ -100,15 +100,17 @@ static int launch_ell(int nrow, int width, const int* col, const V* val, const V
 // COO may hold the same row anywhere else (the reference uses `omp atomic` for the same reason,
 // src/mat_vec.cpp:36-39).  A row-sorted COO (every generator, most .mtx files) therefore issues
 // about one atomic per 16 entries or per row, whichever is shorter; an unsorted one, one per
-// entry, and is bound by the DRAM traffic of 134 MB of x and y touched at random (2.7 ms on the
-// 8M x 8M matrix, DRAM 10.9 GB read + 2.6 GB written; evict-last hints on x and y changed nothing).
+// entry, and is bound by the DRAM traffic of 134 MB of x and y touched at random (2.9 ms on the
+// 8M x 8M matrix, DRAM 10.9 GB read + 2.6 GB written; evict-last hints on x and y changed nothing) -
+// such matrices take the two-phase path further down (2.0 ms).
 // The earlier version combined equal adjacent rows with a segmented warp scan every 32 entries:
 // 72 % of the issue slots on the sorted 256^3 stencil (1.90 ms, profiles/r01_ncu_final_stencil.txt).
 // Order: left to right inside a lane's run, atomics in arbitrary order - the reference's own
 // order is unspecified under OpenMP.
 static constexpr int kCooIPT = 16;   // entries owned by a lane
 
-template <bool kVec>
+// kProducts: `val` already holds the products val*x (phase 2 of the two-phase path below); col and x are not read.
+template <bool kVec, bool kProducts>
 __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict__ row, const int* __restrict__ col,
                                                   const double* __restrict__ val, const double* __restrict__ x,
                                                   double* __restrict__ y)
@@ -127,14 +129,16 @@ __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict
     for (int h = 0; h < kCooIPT; h += 8) {
         int cc[8];
         double xx[8], vv[8];
-        load_block8<kVec>(col + e + h, n - h, cc, pol);
+        if (!kProducts) {
+            load_block8<kVec>(col + e + h, n - h, cc, pol);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xx[k] = h + k < n ? ld_gather(x + cc[k]) : 0.0;
+            for (int k = 0; k < 8; ++k) xx[k] = h + k < n ? ld_gather(x + cc[k]) : 0.0;
+        }
         load_block8<kVec>(val + e + h, n - h, vv, pol);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (h + k < n) {
-                const double p = mul_rn(vv[k], xx[k]);
+                const double p = kProducts ? vv[k] : mul_rn(vv[k], xx[k]);
                 if (rr[h + k] != cur) {
                     atomicAdd(y + cur, sum);
                     cur = rr[h + k];
@@ -146,6 +150,52 @@ __global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict
         }
     }
     atomicAdd(y + cur, sum);
+}
+
+// Two-phase path for a large COO whose rows AND columns jump at random (the 8M x 8M uniform matrix): the fused kernel
+// above touches x and y at random at the same time, 134 MB together against an L2 that holds ~60 MB of randomly
+// accessed data per die, and moves 13.5 GB through DRAM for 2.3 GB of algorithmic bytes (L2 hit rate 28 %).  Taking
+// the entries slab by slab, first all products p = val * x[col] (only x is touched at random), then the scatter
+// y[row] += p (only y), halves the random working set of each kernel at the price of writing and re-reading 8 bytes
+// per entry.  Same arithmetic (one rounded product per entry, runs of equal rows added left to right, atomics).
+static constexpr int kCooSlab = 1 << 25;   // entries per slab: 256 MB of products in scratch slot 3
+
+__global__ void __launch_bounds__(256) coo_product_kernel(int n, const int* __restrict__ col, const double* __restrict__ val,
+                                                          const double* __restrict__ x, double* __restrict__ prod)
+{
+    // coalesced: a CTA owns 2048 consecutive entries, thread t takes t, t+256, ... - eight gathers in flight
+    const int base = blockIdx.x * 2048 + threadIdx.x;
+    const uint64_t pol = policy_evict_first();
+    int c[8];
+    double v[8], g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = base + k * 256 < n ? ld_stream_ef(col + base + k * 256, pol) : 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = base + k * 256 < n ? ld_gather(x + c[k]) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = base + k * 256 < n ? ld_stream_ef(val + base + k * 256, pol) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (base + k * 256 < n) __stcs(prod + base + k * 256, mul_rn(v[k], g[k]));
+}
+
+// 1024 probes spread over the entries: how many neighbours jump by more than 4096 rows / columns, and how many rows
+// fall into the first 1/64 of the matrix (16 expected when rows are uniform; ~200 on an R-MAT matrix, whose scatter is
+// bound by atomics on a few hub rows and gains nothing from the two-phase path: 6.0 vs 6.3 ms)
+__global__ void __launch_bounds__(1024) coo_probe_kernel(int nrow, int nnz, const int* __restrict__ row,
+                                                         const int* __restrict__ col, int* __restrict__ out)
+{
+    const int64_t i = (int64_t)threadIdx.x * (nnz - 1) / 1024;
+    const int r = row[i];
+    const int dr = row[i + 1] - r, dc = col[i + 1] - col[i];
+    const int jr = __syncthreads_count(dr < 0 || dr > 4096);
+    const int jc = __syncthreads_count(dc < 0 || dc > 4096);
+    const int head = __syncthreads_count(r < nrow / 64);
+    if (threadIdx.x == 0) {
+        out[0] = jr;
+        out[1] = jc;
+        out[2] = head;
+    }
 }
 
 // ============================================================================ CSC ==========
@@ -348,16 +398,65 @@ int thsp_ell_spmv_f32(int nrow, int ncol, int width, const int* col_ind, const f
                : launch_ell<float, 1>(nrow, width, col_ind, val, x, y, s);
 }
 
+// Does this COO jump at random in both index arrays, without hub rows?  Probed once per (array, size) and remembered: both paths are
+// correct for any input, so a stale answer can only cost time.
+static bool coo_is_scattered(int nrow, int nnz, const int* row_ind, const int* col_ind, cudaStream_t s)
+{
+    struct Seen { const int* row; const int* col; int nnz; bool scattered; };
+    static Seen seen[8] = {};
+    static int next = 0;
+    for (const Seen& e : seen)
+        if (e.row == row_ind && e.col == col_ind && e.nnz == nnz) return e.scattered;
+    int* d = static_cast<int*>(scratch(3 * sizeof(int), 1));
+    int h[3] = {0, 0, 0};
+    if (!d) return false;
+    coo_probe_kernel<<<1, 1024, 0, s>>>(nrow, nnz, row_ind, col_ind, d);
+    note_launch();
+    if (cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const bool scattered = h[0] > 256 && h[1] > 256 && h[2] <= 80;
+    seen[next] = Seen{row_ind, col_ind, nnz, scattered};
+    next = (next + 1) % 8;
+    return scattered;
+}
+
 int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
                       const double* x, double* y, thsp_stream_t stream)
 {
-    (void)nrow; (void)ncol;
+    static const int env_two_phase = getenv("THSP_COO_TWO_PHASE") ? atoi(getenv("THSP_COO_TWO_PHASE")) : -1;   // -1 = decide
+    return thsp_coo_spmv_path_f64(env_two_phase, nrow, ncol, nnz, row_ind, col_ind, val, x, y, stream);
+}
+
+int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
+                           const double* x, double* y, thsp_stream_t stream)
+{
     if (ensure_device()) return 1;
     if (nnz <= 0) return 0;
-    const int grid = div_up(div_up(nnz, kCooIPT), 256);
+    cudaStream_t s = as_stream(stream);
     const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)col_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads
-    if (vec) coo_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
-    else coo_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(nnz, row_ind, col_ind, val, x, y);
+    bool two_phase = path > 0;
+    if (path < 0)   // x and y together well beyond what L2 keeps of randomly accessed data, enough entries to matter
+        two_phase = nnz >= (1 << 24) && ((size_t)nrow + (size_t)ncol) * sizeof(double) > ((size_t)96 << 20) &&
+                    coo_is_scattered(nrow, nnz, row_ind, col_ind, s);
+    if (two_phase) {
+        double* prod = static_cast<double*>(scratch(sizeof(double) * (size_t)std::min(nnz, kCooSlab), 3));
+        if (!prod) return 1;
+        for (int e0 = 0; e0 < nnz; e0 += kCooSlab) {
+            const int n = std::min(kCooSlab, nnz - e0);
+            coo_product_kernel<<<div_up(n, 2048), 256, 0, s>>>(n, col_ind + e0, val + e0, x, prod);
+            THSP_LAUNCH_CHECK();
+            const int grid = div_up(div_up(n, kCooIPT), 256);
+            if (vec) coo_kernel<true, true><<<grid, 256, 0, s>>>(n, row_ind + e0, nullptr, prod, nullptr, y);
+            else coo_kernel<false, true><<<grid, 256, 0, s>>>(n, row_ind + e0, nullptr, prod, nullptr, y);
+            THSP_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    const int grid = div_up(div_up(nnz, kCooIPT), 256);
+    if (vec) coo_kernel<true, false><<<grid, 256, 0, s>>>(nnz, row_ind, col_ind, val, x, y);
+    else coo_kernel<false, false><<<grid, 256, 0, s>>>(nnz, row_ind, col_ind, val, x, y);
     THSP_LAUNCH_CHECK();
     return 0;
 }

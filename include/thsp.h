@@ -131,6 +131,11 @@ THSP_API int thsp_ell_spmv_f32(int nrow, int ncol, int width, const int* col_ind
 /* COOMatirxMatVector [sic] (src/mat_vec.cpp:18-42): y[row[k]] += val[k]*x[col[k]]. */
 THSP_API int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
                                const double* x, double* y, thsp_stream_t stream);
+/* The same with the path named (tests, benches): 0 = one kernel (products and scatter fused), 1 = slab by slab, all
+ * products first (only x touched at random), then the scatter (only y) - what thsp_coo_spmv_f64 picks for large
+ * matrices whose rows and columns both jump at random; -1 = let the library decide as thsp_coo_spmv_f64 does. */
+THSP_API int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind,
+                                    const double* val, const double* x, double* y, thsp_stream_t stream);
 /* CSCMatrixMatVector (src/mat_vec.cpp:69-95): column scatter y[row[j]] += val[j]*x[c]. */
 THSP_API int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int* row_ind, const double* val,
                                const double* x, double* y, thsp_stream_t stream);

@@ -238,6 +238,24 @@ def test_formats_synthetic(thsp, cuda, oracle, which):
         assert_bits(host(Y.values), oracle.dia_spmv(nrow, ncol, off, dv, x, y0), f"dia {which}")
 
 
+@pytest.mark.parametrize("nnz", [0, 1, 15, 16, 17, 2047, 2048, 2049, 100_003])
+@pytest.mark.parametrize("path", [0, 1])
+def test_coo_paths_match_oracle(thsp, cuda, oracle, nnz, path):
+    """Both COO paths (fused; products then scatter) against COOMatirxMatVector (src/mat_vec.cpp:18-42) around the
+    kernels' block sizes (16 entries per lane, 2048 per CTA of the product kernel), y += semantics, unsorted entries."""
+    lib = thsp.load()
+    nrow, ncol = 5000, 4000
+    ri, cj, v = oracle.gen_uniform_coo(nrow, ncol, max(nnz, 1), 43)
+    ri, cj, v = ri[:nnz], cj[:nnz], v[:nnz]
+    x = oracle.gen_vector(ncol, 5); y0 = oracle.gen_vector(nrow, 6) - 0.5
+    y = dev(y0.copy()); d_ri, d_cj, d_v, d_x = dev(ri), dev(cj), dev(v), dev(x)
+    thsp.lib.check(lib.thsp_coo_spmv_path_f64(path, nrow, ncol, nnz, thsp.lib.ptr(d_ri), thsp.lib.ptr(d_cj), thsp.lib.ptr(d_v),
+                                              thsp.lib.ptr(d_x), thsp.lib.ptr(y), thsp.lib.current_stream()))
+    torch.cuda.synchronize()
+    ref = oracle.coo_spmv(nrow, ncol, ri, cj, v, x, y0)
+    assert max_row_error(host(y), ref, row_scale_coo(nrow, ri, cj, v, x), y0) <= TOL64
+
+
 def test_coo_sorted_uses_carry(thsp, cuda, oracle):
     """Row-sorted COO: same answer as CSR within tolerance (segments chained across steps)."""
     from arm_spmv_b200 import host as H
