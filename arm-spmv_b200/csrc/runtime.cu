@@ -222,6 +222,7 @@ int thsp_scratch_release(void)
         if (sc.p) cudaFree(sc.p);
         sc.p = nullptr;
         sc.cap = 0;
+        ++sc.uses;   // whoever remembered a pointer into this slot must notice (thsp_coo2ell_prepare)
     }
     return 0;
 }

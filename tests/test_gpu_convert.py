@@ -140,7 +140,8 @@ def test_exclusive_scan(thsp, cuda, n):
     assert_bits(host(d), want, f"scan in place {n}")
 
 
-@pytest.mark.parametrize("between", ["nothing", "other_conversion", "merge_spmv", "other_width", "other_arrays", "no_prepare"])
+@pytest.mark.parametrize("between", ["nothing", "other_conversion", "merge_spmv", "scratch_release", "other_width", "other_arrays",
+                                     "no_prepare"])
 def test_ell_two_step_conversion(thsp, cuda, oracle, between):
     """thsp_coo2ell_prepare keeps the row sort in the library's scratch for the thsp_coo2ell that follows; whatever
     happens in between (another conversion, a kernel that borrows the same scratch, different arguments, no prepare at
@@ -164,6 +165,8 @@ def test_ell_two_step_conversion(thsp, cuda, oracle, between):
         R = H.CSRMatrix(H.rmat_coo(12, 40000, 3))
         x = H.gen_vector(R.ncol, 1); y = H.Vector(R.nrow); y.Fill(0.0)
         H.csr_spmv_kernel(4, 1, R, x.values, y.values, True)
+    elif between == "scratch_release":     # the buffers the prepare step filled are gone
+        chk(lib.thsp_scratch_release())
     elif between == "other_arrays":        # same contents at other addresses: nothing to reuse
         src = H.COOMatrix(nrow, ncol, ri.copy(), ci.copy(), va.copy())
     width = k + 3 if between == "other_width" else k
