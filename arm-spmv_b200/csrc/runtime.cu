@@ -144,6 +144,17 @@ int thsp_malloc_host(void** ptr, size_t bytes)
     THSP_CUDA(cudaMallocHost(ptr, bytes ? bytes : 16));
     return 0;
 }
+int thsp_host_register(void* ptr, size_t bytes)
+{
+    if (ensure_device()) return 1;
+    THSP_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int thsp_host_unregister(void* ptr)
+{
+    if (ptr) THSP_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
 int thsp_free(void* ptr)
 {
     if (ptr) THSP_CUDA(cudaFree(ptr));

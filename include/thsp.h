@@ -52,6 +52,10 @@ THSP_API int thsp_sm_count(int* count);
 THSP_API int thsp_malloc(void** ptr, size_t bytes);
 THSP_API int thsp_malloc_managed(void** ptr, size_t bytes);
 THSP_API int thsp_malloc_host(void** ptr, size_t bytes); /* pinned */
+/* Page-lock host memory the caller already owns (a shared-memory segment holding x for all the processes of a box):
+ * copies from it run at pinned-memory speed and may be captured into the host-buffer SpMV's CUDA graph. */
+THSP_API int thsp_host_register(void* ptr, size_t bytes);
+THSP_API int thsp_host_unregister(void* ptr);
 THSP_API int thsp_free(void* ptr);
 THSP_API int thsp_free_host(void* ptr);
 /* 0 = plain host (or unknown), 1 = device, 2 = managed, 3 = pinned host */

@@ -77,3 +77,40 @@ def test_two_virtual_ranks(thsp, cuda, n_total, halo):
         if it == 1:
             untouched = ranks[1].x[: per - h1]
             assert bool(torch.isnan(untouched).all()) or untouched.numel() == 0
+
+
+@pytest.mark.parametrize("n,rank,world", [(160, 0, 1), (144, 1, 3)])
+def test_host_vector_shared_by_the_ranks(thsp, cuda, oracle, n, rank, world):
+    """The distributed y = A x with x in ONE page-locked host vector (power.SharedHostVector, e2e_spmv_step_shared): a
+    rank's row blocks pull their windows of x from it through thsp_csr_plan_spmv_host_f64.  One process plays rank
+    `rank` of `world`: its slice of y must equal the oracle's rows bit for bit, and only its window of x may have
+    been uploaded."""
+    from arm_spmv_b200 import power
+    ops = power.CudaOps(torch.device("cuda", 0))
+    A = power.PartitionedCSR.stencil27(n, rank, world, ops, max_block_rows=3_000_000)
+    N = n ** 3
+    x = oracle.gen_vector(N, 9)
+    xs = power.SharedHostVector(N, 0, 1, torch.device("cuda", 0), tag=f"test{n}")
+    try:
+        xs.tensor.copy_(torch.from_numpy(x))
+        yh = torch.full((A.count,), float("nan"), dtype=torch.float64).pin_memory()
+
+        class It:   # the fields e2e_spmv_step_shared reads
+            pass
+        it = It()
+        it.A, it.ops = A, ops
+        it.x = torch.full((N,), float("nan"), dtype=torch.float64, device="cuda")
+        it.y = torch.empty(A.count, dtype=torch.float64, device="cuda")
+        for _ in range(3):   # eager, captured, replayed
+            yh.fill_(float("nan"))
+            power.e2e_spmv_step_shared(it, xs.tensor, yh)
+            rp, ci, va = oracle.gen_stencil27_csr(n, A.start, A.start + A.count)
+            ref = oracle.csr_spmv(A.count, N, rp, ci, va, x, np.zeros(A.count))
+            assert yh.numpy().tobytes() == ref.tobytes()
+        up = torch.nonzero(~torch.isnan(it.x.cpu())).flatten()
+        lo = min(b.col_min for b in A.blocks); hi = max(b.col_max for b in A.blocks)   # conservative bounds of the blocks
+        first, last = int(up[0]), int(up[-1])
+        assert up.numel() == last - first + 1, "the uploaded window has holes"
+        assert lo <= first <= max(0, A.start - n * n) and min(N - 1, A.start + A.count - 1 + n * n) <= last <= hi
+    finally:
+        xs.close()
