@@ -69,7 +69,9 @@ def spmv_all(A, name, ell=True, dia=False, kernels=()):
         ms = timeit(lambda: H.ELLMatrixMatVector(D, x, y)); report(f"{name}: ELL", ms, nrow * K * 12 + ncol * 8 + 2 * nrow * 8, fl)
         del D
     if dia:
+        ms = timeit(lambda: H.DIAMatrix(B), reps=3, warm=1)
         E = H.DIAMatrix(B)
+        report(f"{name}: CSR->DIA (ndiags={E.ndiags})", ms, nnz * 12 + (nrow + 1) * 4 + nrow * E.ndiags * 8)
         ms = timeit(lambda: H.DIAMatrixMatVector(E, x, y)); report(f"{name}: DIA (ndiags={E.ndiags})", ms, nrow * E.ndiags * 8 + ncol * 8 + 2 * nrow * 8, fl)
     if B.values.dtype == torch.float64:
         B32 = H.CSRMatrix(nrow=nrow, ncol=ncol, row_ptr=B.row_ptr, col_ind=B.col_ind, values=B.values.to(torch.float32))

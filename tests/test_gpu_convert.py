@@ -178,6 +178,51 @@ def test_ell_two_step_conversion(thsp, cuda, oracle, between):
     assert_bits(host(oc), eco, f"ell col ({between})"); assert_bits(host(ov), eva, f"ell val ({between})")
 
 
+@pytest.mark.parametrize("between", ["nothing", "other_count", "scratch_release", "other_conversion"])
+@pytest.mark.parametrize("shape", ["banded", "many_diagonals", "hub_row"])
+def test_dia_count_then_emit(thsp, cuda, oracle, between, shape):
+    """DIAMatrix(const CSRMatrix&) (src/matrix.cpp:673-726) as the library does it: count the diagonals, allocate, emit
+    the offsets (reusing the marks of the counting call when nothing touched them in between), fill.  Banded rows go
+    through the shared-memory fill, > 152 diagonals through the plain one, a hub row past the staged entries."""
+    from arm_spmv_b200 import host as H
+    lib = thsp.load(); chk = thsp.lib.check; ptr = thsp.lib.ptr; cs = thsp.lib.current_stream
+    rs = np.random.RandomState(11)
+    if shape == "banded":
+        nrow = ncol = 6000
+        ri = np.repeat(np.arange(nrow, dtype=np.int32), 7); ci = (ri + rs.randint(-9, 10, ri.size)).clip(0, ncol - 1).astype(np.int32)
+    elif shape == "many_diagonals":
+        nrow, ncol = 700, 650
+        ri = rs.randint(0, nrow, 9000).astype(np.int32); ci = rs.randint(0, ncol, 9000).astype(np.int32)
+    else:   # one row with 6000 entries (more than a CTA stages), duplicates included, others short
+        nrow = ncol = 3000
+        ri = np.concatenate([np.full(6000, 5, np.int32), rs.randint(0, nrow, 4000).astype(np.int32)])
+        ci = np.concatenate([(5 + rs.randint(-60, 61, 6000)).clip(0, ncol - 1), (ri[6000:] + rs.randint(-60, 61, 4000)).clip(0, ncol - 1)]).astype(np.int32)
+    keep = ~((ri == 0) & (ci == ncol - 1))
+    ri, ci = ri[keep], ci[keep]
+    va = rs.uniform(-1, 1, ri.size)
+    rp, co, cv, _ = oracle.coo2csr(nrow, ncol, ri, ci, va)
+    off, dv = oracle.csr2dia(nrow, ncol, rp, co, cv)
+    d_rp, d_co, d_cv = dev(rp), dev(co), dev(cv)
+    nd = ctypes.c_int(0)
+    chk(lib.thsp_csr2dia_offsets(nrow, ncol, ptr(d_rp), ptr(d_co), ctypes.byref(nd), None, 0, cs()))
+    assert nd.value == len(off)
+    if between == "other_count":
+        o_rp, o_co = dev(np.array([0, 1, 2, 2], np.int32)), dev(np.array([0, 2], np.int32))   # (0,0) and (1,2): offsets 0, +1
+        k = ctypes.c_int(0)
+        chk(lib.thsp_csr2dia_offsets(3, 3, ptr(o_rp), ptr(o_co), ctypes.byref(k), None, 0, cs()))
+        assert k.value == 2
+    elif between == "scratch_release":
+        chk(lib.thsp_scratch_release())
+    elif between == "other_conversion":
+        H.CSCMatrix(H.COOMatrix(nrow, ncol, ri, ci, va)); H.ELLMatrix(H.COOMatrix(50, 50, ri[:40] % 50, ci[:40] % 50, va[:40]))
+    d_off = torch.full((nd.value,), -12345, dtype=torch.int32, device="cuda")
+    d_val = torch.full((nrow * nd.value,), float("nan"), dtype=torch.float64, device="cuda")
+    chk(lib.thsp_csr2dia_offsets(nrow, ncol, ptr(d_rp), ptr(d_co), ctypes.byref(nd), ptr(d_off), nd.value, cs()))
+    assert nd.value == len(off)
+    chk(lib.thsp_csr2dia_fill(nrow, ncol, ptr(d_rp), ptr(d_co), ptr(d_cv), nd.value, ptr(d_off), ptr(d_val), cs()))
+    assert_bits(host(d_off), off, f"dia offsets ({shape}, {between})"); assert_bits(host(d_val), dv, f"dia values ({shape}, {between})")
+
+
 def test_generators_match_cpu_twins(thsp, cuda, oracle):
     from arm_spmv_b200 import host as H
     A = H.stencil27_csr(9)
