@@ -588,8 +588,11 @@ __device__ __forceinline__ void diag_flags(int n, int base, const int* __restric
         for (int i = 0; i < kScanItems; ++i) f[i] = base + i < n && ri[base + i] == ci[base + i];
     }
 }
+// The counting pass leaves one bit per entry (row == col) for the placing pass: four words per warp, bit l of word i =
+// entry 4*l + i of the warp's 128, so the placing pass reads 16 bytes per 128 entries instead of both index arrays again
+// (256^3 stencil: 1.49 -> see profiles/; the index arrays are 3.6 GB there).
 __global__ void __launch_bounds__(kScanThreads) diag_count_kernel(int n, const int* __restrict__ ri, const int* __restrict__ ci,
-                                                                  int* __restrict__ bcnt)
+                                                                  int* __restrict__ bcnt, unsigned* __restrict__ flags)
 {
     __shared__ int tot;
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -598,26 +601,41 @@ __global__ void __launch_bounds__(kScanThreads) diag_count_kernel(int n, const i
     int s = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) s += f[i];
+    if (flags) {
+        const int warp = (blockIdx.x * kScanThreads + threadIdx.x) >> 5;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const unsigned w = __ballot_sync(0xffffffffu, f[i]);
+            if ((threadIdx.x & 31) == i) flags[(size_t)warp * kScanItems + i] = w;
+        }
+    }
     block_exclusive_scan(s, &tot);
     if (threadIdx.x == 0) bcnt[blockIdx.x] = tot;
 }
-__global__ void __launch_bounds__(kScanThreads) diag_scatter_kernel(int n, const int* __restrict__ ri, const int* __restrict__ ci,
+__global__ void __launch_bounds__(kScanThreads) diag_scatter_kernel(int n, const unsigned* __restrict__ flags,
                                                                     const double* __restrict__ val, const int* __restrict__ boff,
                                                                     int cap, double* __restrict__ diag)
 {
     __shared__ int tot;
     if (boff[blockIdx.x + 1] == boff[blockIdx.x]) return;   // no diagonal entry in this tile: nothing to read again
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    const int warp = (blockIdx.x * kScanThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    unsigned w = lane < kScanItems ? flags[(size_t)warp * kScanItems + lane] : 0u;
     bool f[kScanItems];
-    diag_flags(n, base, ri, ci, f);
     int s = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) s += f[i];
+    for (int i = 0; i < kScanItems; ++i) {
+        f[i] = (__shfl_sync(0xffffffffu, w, i) >> lane) & 1u;
+        s += f[i];
+    }
+    double v[kScanItems];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) v[i] = f[i] ? val[base + i] : 0.0;   // issued before the scan's barriers
     int pos = block_exclusive_scan(s, &tot) + boff[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i)
         if (f[i]) {
-            if (pos < cap) diag[pos] = val[base + i];
+            if (pos < cap) diag[pos] = v[i];
             ++pos;
         }
 }
@@ -630,14 +648,16 @@ static int pack_diagonal(int nnz, const int* ri, const int* ci, const double* va
         return 0;
     }
     const int nb = div_up(nnz, kScanTile);
-    int* bcnt = static_cast<int*>(scratch(sizeof(int) * (2 * (size_t)nb + 2), 4));
+    const size_t nflag = diag ? (size_t)nb * (kScanThreads / 32) * kScanItems : 0;
+    int* bcnt = static_cast<int*>(scratch(sizeof(int) * (2 * (size_t)nb + 2 + nflag), 4));
     if (!bcnt) return 1;
     int* boff = bcnt + nb;
-    diag_count_kernel<<<nb, kScanThreads, 0, s>>>(nnz, ri, ci, bcnt);
+    unsigned* flags = diag ? reinterpret_cast<unsigned*>(boff + nb + 2) : nullptr;
+    diag_count_kernel<<<nb, kScanThreads, 0, s>>>(nnz, ri, ci, bcnt, flags);
     THSP_LAUNCH_CHECK();
     if (exclusive_scan(nb, bcnt, boff, s)) return 1;
     if (diag) {
-        diag_scatter_kernel<<<nb, kScanThreads, 0, s>>>(nnz, ri, ci, val, boff, cap, diag);
+        diag_scatter_kernel<<<nb, kScanThreads, 0, s>>>(nnz, flags, val, boff, cap, diag);
         THSP_LAUNCH_CHECK();
     }
     if (ndiag_host) {
