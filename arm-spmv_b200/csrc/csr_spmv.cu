@@ -640,6 +640,9 @@ struct HostPipe {
     const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
     int key_acc = -1, key_seen = 0;
     unsigned kernels_per_call = 0;
+    // the kernel choice the chunks and the graph were built for (thsp_csr_plan_set_kernel / _set_stream_config /
+    // _autotune may change it afterwards: the pipeline is then rebuilt)
+    int built_kernel = 0, built_lanes = 0, built_ctas = 0, built_warps = 0, built_stages = 0, built_chunk = 0;
     // THSP_HOST_TRACE=1: timing events per chunk (x piece in, kernel start / end, y piece out), printed after the call
     cudaEvent_t t_begin = nullptr;
     std::vector<cudaEvent_t> t_in, t_k0, t_k1, t_out;
@@ -798,20 +801,26 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
     return 0;
 }
 
+static void drop_host_pipe(thsp_csr_plan* plan)
+{
+    HostPipe* hp = plan->pipe;
+    if (!hp) return;
+    for (auto* v : {&hp->in_done, &hp->k_done, &hp->t_in, &hp->t_k0, &hp->t_k1, &hp->t_out})
+        for (auto e : *v) cudaEventDestroy(e);
+    if (hp->begin) cudaEventDestroy(hp->begin);
+    if (hp->out_done) cudaEventDestroy(hp->out_done);
+    if (hp->t_begin) cudaEventDestroy(hp->t_begin);
+    if (hp->exec) cudaGraphExecDestroy(hp->exec);
+    if (hp->s_cap) cudaStreamDestroy(hp->s_cap);
+    if (hp->s_in) cudaStreamDestroy(hp->s_in);
+    if (hp->s_out) cudaStreamDestroy(hp->s_out);
+    delete hp;
+    plan->pipe = nullptr;
+}
+
 int thsp_csr_plan_destroy(thsp_csr_plan* plan)
 {
-    if (plan && plan->pipe) {
-        HostPipe* hp = plan->pipe;
-        for (auto e : hp->in_done) cudaEventDestroy(e);
-        for (auto e : hp->k_done) cudaEventDestroy(e);
-        if (hp->begin) cudaEventDestroy(hp->begin);
-        if (hp->out_done) cudaEventDestroy(hp->out_done);
-        if (hp->exec) cudaGraphExecDestroy(hp->exec);
-        if (hp->s_cap) cudaStreamDestroy(hp->s_cap);
-        if (hp->s_in) cudaStreamDestroy(hp->s_in);
-        if (hp->s_out) cudaStreamDestroy(hp->s_out);
-        delete hp;
-    }
+    if (plan) drop_host_pipe(plan);
     if (plan && plan->merge_part) cudaFree(plan->merge_part);
     delete plan;
     return 0;
@@ -973,6 +982,8 @@ static int build_host_pipe(thsp_csr_plan* p, cudaStream_t s)
         THSP_CUDA(cudaEventCreateWithFlags(&hp->in_done[c], cudaEventDisableTiming));
         THSP_CUDA(cudaEventCreateWithFlags(&hp->k_done[c], cudaEventDisableTiming));
     }
+    hp->built_kernel = p->kernel; hp->built_lanes = p->lanes; hp->built_ctas = p->ctas;
+    hp->built_warps = p->stream_cfg.warps; hp->built_stages = p->stream_cfg.stages; hp->built_chunk = p->stream_cfg.chunk;
     p->pipe = hp;
     return 0;
 }
@@ -1057,6 +1068,14 @@ int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host
     thsp_csr_plan* plan = const_cast<thsp_csr_plan*>(cplan);
     cudaStream_t s = as_stream(stream);
     if (plan->nrow <= 0) return 0;
+    if (plan->pipe) {
+        const HostPipe* b = plan->pipe;
+        if (b->built_kernel != plan->kernel || b->built_lanes != plan->lanes || b->built_ctas != plan->ctas ||
+            b->built_warps != plan->stream_cfg.warps || b->built_stages != plan->stream_cfg.stages || b->built_chunk != plan->stream_cfg.chunk) {
+            THSP_CUDA(cudaStreamSynchronize(s));
+            drop_host_pipe(plan);
+        }
+    }
     if (!plan->pipe && build_host_pipe(plan, s)) return 1;
     HostPipe* hp = plan->pipe;
     static const int env_trace = getenv("THSP_HOST_TRACE") ? atoi(getenv("THSP_HOST_TRACE")) : 0;

@@ -292,9 +292,12 @@ def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
     yh_other = torch.from_numpy(y0.copy()).pin_memory()
     y_pageable = y0.copy()
     # call 1 runs eagerly and builds the pipeline, call 2 captures it as a CUDA graph, calls 3-4 replay the graph,
-    # call 5 brings another pinned y (graph dropped, eager again), call 6 a pageable y (never captured)
-    for it in range(6):
-        yh = yh_first if it < 4 else (yh_other if it == 4 else torch.from_numpy(y_pageable))
+    # call 5 brings another pinned y (graph dropped, eager again), call 6 a pageable y (never captured); before calls 7-9
+    # the plan's launch shape changes, so the chunks and the graph are rebuilt
+    for it in range(9):
+        if it == 6:
+            thsp.lib.check(lib.thsp_csr_plan_set_stream_config(A.plan(), 0, 0, 0, 100))
+        yh = yh_first if (it < 4 or it > 5) else (yh_other if it == 4 else torch.from_numpy(y_pageable))
         yh.copy_(torch.from_numpy(y0))
         thsp.lib.check(lib.thsp_csr_plan_spmv_host_f64(A.plan(), ctypes.c_void_p(xh.data_ptr()), ctypes.c_void_p(yh.data_ptr()),
                                                        thsp.lib.ptr(xd), thsp.lib.ptr(yd), 1 if accumulate else 0, thsp.lib.current_stream()))
