@@ -223,6 +223,24 @@ def test_dia_count_then_emit(thsp, cuda, oracle, between, shape):
     assert_bits(host(d_off), off, f"dia offsets ({shape}, {between})"); assert_bits(host(d_val), dv, f"dia values ({shape}, {between})")
 
 
+@pytest.mark.parametrize("hub", [0, 4999, 9000])
+def test_ell_long_rows(thsp, cuda, oracle, hub):
+    """ELLMatrix(const COOMatrix&) when rows average >= 20 entries (the kernel that stages a CTA's entries in shared
+    memory), without and with one row longer than the stage (4096 entries)."""
+    from arm_spmv_b200 import host as H
+    rs = np.random.RandomState(hub + 1)
+    nrow, ncol = 300, 12000
+    ri = np.repeat(np.arange(nrow, dtype=np.int32), 24)
+    if hub:
+        ri = np.concatenate([ri, np.full(hub, 137, np.int32)])
+    rs.shuffle(ri)
+    ci = rs.randint(0, ncol, ri.size).astype(np.int32); va = rs.uniform(-1, 1, ri.size)
+    D = H.ELLMatrix(H.COOMatrix(nrow, ncol, ri, ci, va))
+    k, eco, eva, _ = oracle.coo2ell(nrow, ncol, ri, ci, va)
+    assert D.nonzeros_in_row == k == 24 + hub
+    assert_bits(host(D.col_ind), eco, "ell col"); assert_bits(host(D.values), eva, "ell val")
+
+
 def test_generators_match_cpu_twins(thsp, cuda, oracle):
     from arm_spmv_b200 import host as H
     A = H.stencil27_csr(9)
