@@ -11,6 +11,7 @@ namespace thsp {
 // ---- error plumbing: C ABI returns codes, the message is kept per thread ---------------
 void set_error(const char* fmt, ...);
 void note_launch(unsigned n = 1);
+void forget_launches(unsigned n);   // kernels that were captured into a graph, not launched
 
 #define THSP_CUDA(call)                                                                              \
     do {                                                                                             \

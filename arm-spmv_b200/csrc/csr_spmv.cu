@@ -1107,7 +1107,7 @@ int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host
         const int rc = host_pipe_enqueue(plan, x_host, y_host, x_dev, y_dev, accumulate, hp->s_cap);
         const cudaError_t e = cudaStreamEndCapture(hp->s_cap, &g);
         hp->kernels_per_call = (unsigned)(thsp_launch_count() - before);
-        note_launch(0u - hp->kernels_per_call);   // captured, not launched
+        forget_launches(hp->kernels_per_call);   // captured, not launched
         if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&hp->exec, g, 0) != cudaSuccess) hp->exec = nullptr;
         if (g) cudaGraphDestroy(g);
         if (rc != 0 || e != cudaSuccess) {

@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 void note_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void forget_launches(unsigned n) { g_launches.fetch_sub(n, std::memory_order_relaxed); }
 
 int ensure_device()
 {

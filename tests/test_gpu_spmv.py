@@ -294,6 +294,7 @@ def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
     # call 1 runs eagerly and builds the pipeline, call 2 captures it as a CUDA graph, calls 3-4 replay the graph,
     # call 5 brings another pinned y (graph dropped, eager again), call 6 a pageable y (never captured); before calls 7-9
     # the plan's launch shape changes, so the chunks and the graph are rebuilt
+    launches0 = thsp.lib.launch_count()
     for it in range(9):
         if it == 6:
             thsp.lib.check(lib.thsp_csr_plan_set_stream_config(A.plan(), 0, 0, 0, 100))
@@ -310,3 +311,5 @@ def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
             assert_bits(yh.numpy(), ref, f"host path {which} acc={accumulate}")
         else:
             assert max_row_error(yh.numpy(), ref, row_scale_csr(nrow, rp, ci, va, x), y0 if accumulate else None) <= TOL64
+    # the launch counter counts graph replays kernel by kernel and does not count the capture itself
+    assert 9 <= thsp.lib.launch_count() - launches0 < 1000
