@@ -479,16 +479,20 @@ __global__ void __launch_bounds__(256) boundaries_kernel(int n, int nbuckets, co
             for (int j = 0; j < kBndItems; ++j) k[1 + j] = p0 + j < n ? ld_stream(key + p0 + j) : nbuckets;
         }
         if (k[0] != k[kBndItems]) {   // keys do not decrease: equal ends = one bucket throughout, nothing starts here
+            // position n carries the sentinel nbuckets; p0 + j <= n fits an int; the clamps only matter for indices outside
+            // [0, nbuckets), which must not turn into stores outside ptr[]
+            const int valid = (int)min((int64_t)kBndItems, (int64_t)n + 1 - p0);
+            const int pb = (int)p0;
 #pragma unroll
             for (int j = 0; j < kBndItems; ++j) {
-                const int64_t p = p0 + j;
-                if (p > n) break;
                 const int lo = max(k[j] + 1, 0), hi = min(k[1 + j], nbuckets);   // fill ptr[lo..hi] with p
-                if (hi - lo >= 8) {
-                    const int q = atomicAdd(&q_n, 1);
-                    q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = (int)p;
-                } else {
-                    for (int r = lo; r <= hi; ++r) ptr[r] = (int)p;
+                if (j < valid && hi >= lo) {
+                    if (hi - lo >= 8) {
+                        const int q = atomicAdd(&q_n, 1);
+                        q_lo[q] = lo; q_hi[q] = hi; q_pos[q] = pb + j;
+                    } else {
+                        for (int r = lo; r <= hi; ++r) ptr[r] = pb + j;
+                    }
                 }
             }
         }
