@@ -230,3 +230,41 @@ def test_partition_matches_reference_rule(oracle):
     for n, parts in [(10, 3), (64, 8), (7, 7), (5, 8)]:
         for p in range(parts):
             assert power.partition_rows(n, parts, p) == oracle.partition(n, parts, p)
+
+
+def _shared_vector_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arm_spmv_b200 import power
+        dev = torch.device("cpu")
+        assert power._all_ok(True, world, None, dev) is True
+        assert power._all_ok(rank != 1, world, None, dev) is False      # one rank's failure is everybody's
+        result = "mapped"
+        try:
+            xs = power.SharedHostVector(1000, rank, world, dev, tag="gloo_test")
+            xs.close()
+        except OSError:   # no GPU here: page-locking fails - on every rank, after the same collectives
+            result = "OSError"
+        leftovers = [f for f in os.listdir("/dev/shm") if f.startswith("thsp_gloo_test_")] if os.path.isdir("/dev/shm") else []
+        dist.barrier()
+        with open(os.path.join(out, f"r{rank}.txt"), "w") as f:
+            f.write(result + " " + str(len(leftovers)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_vector_fails_on_all_ranks_together(tmp_path):
+    """power.SharedHostVector (x of the multi-GPU host-buffer call in one /dev/shm segment): when a rank cannot map or
+    page-lock it - as here, without a GPU - every rank raises after the same collectives, nobody hangs, and the segment is
+    removed.  bench.py then keeps the all-gather form of the call."""
+    if not os.path.isdir("/dev/shm"):
+        pytest.skip("no /dev/shm")
+    world, port = 2, 29600 + os.getpid() % 300
+    mp.spawn(_shared_vector_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = [open(os.path.join(str(tmp_path), f"r{r}.txt")).read().split() for r in range(world)]
+    assert got[0][0] == got[1][0], got
+    if not torch.cuda.is_available():
+        assert got[0][0] == "OSError"
+    assert got[0][1] == got[1][1] == "0", "the shared segment was left behind"
