@@ -568,7 +568,9 @@ class SharedHostVector:
         if rank == 0:
             try:
                 with open(self.path, "wb") as f:
-                    f.truncate(n * 8)
+                    # reserve the pages now: a /dev/shm smaller than the vector must fail here (ENOSPC), not with a
+                    # bus error when the vector is first written
+                    os.posix_fallocate(f.fileno(), 0, max(n * 8, 1))
             except OSError:
                 ok = False
         if not _all_ok(ok, world, group, device):
