@@ -116,7 +116,8 @@ __host__ __device__ inline size_t stream_warp_bytes(int stages, int chunk)
 template <typename V>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                      const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH)
+                      const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
+                      V* __restrict__ tile_ss)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -252,7 +253,14 @@ __global__ void __launch_bounds__(768, 1)
         c_stage = (c_stage + 1 == S) ? 0 : c_stage + 1;
         if (c_stage == 0) c_parity ^= 1u;
         if (++c_chunk == c_nch) {
-            if (row < nrow) y[row] = accumulate ? add_rn(yold, sum) : sum;
+            const V ynew = accumulate ? add_rn(yold, sum) : sum;
+            if (row < nrow) y[row] = ynew;
+            if (tile_ss) {   // the tile's partial of sum y_i^2, in the canonical order of tree_sum.cuh: nobody reads y again
+                V q = row < nrow ? mul_rn(ynew, ynew) : V(0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) q = add_rn(q, __shfl_xor_sync(full, q, o));
+                if (lane == 0) tile_ss[c_tile] = q;
+            }
             c_tile += GW;
             c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
             c_chunk = 0;
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(768, 1)
 
 template <typename V>
 static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
-                      const V* x, V* y, int acc, cudaStream_t s)
+                      const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr)
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
@@ -281,7 +289,7 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk);
+    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -703,7 +711,7 @@ static void choose_stateless(int nrow, int nnz, const void* val, const int* col,
 }
 
 template <typename V>
-static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s)
+static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr)
 {
     if (p->nrow <= 0) return 0;
     if (p->kernel == THSP_CSR_MERGE) {
@@ -717,7 +725,7 @@ static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStre
     }
     if (p->kernel == THSP_CSR_STREAM)
         return run_stream<V>(p->stream_cfg, p->ctas, p->nrow, p->nnz, p->row_ptr, p->col_ind,
-                             static_cast<const V*>(p->val), x, y, acc, s);
+                             static_cast<const V*>(p->val), x, y, acc, s, tile_ss);
     return dispatch<V>(p->kernel, p->lanes, &p->stream_cfg, p->nrow, p->ncol, p->nnz, p->row_ptr, p->col_ind,
                        static_cast<const V*>(p->val), x, y, acc, s);
 }
@@ -918,6 +926,15 @@ int thsp_csr_plan_spmv_f64(const thsp_csr_plan* plan, const double* x, double* y
 {
     THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
     return plan_spmv<double>(plan, x, y, accumulate, as_stream(stream));
+}
+int thsp_csr_plan_spmv_sumsq_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate, double* tile_ss,
+                                 thsp_stream_t stream)
+{
+    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
+    THSP_REQUIRE(tile_ss != nullptr, "tile_ss is where the per-tile sums of squares go");
+    if (plan->kernel == THSP_CSR_STREAM) return plan_spmv<double>(plan, x, y, accumulate, as_stream(stream), tile_ss);
+    if (plan_spmv<double>(plan, x, y, accumulate, as_stream(stream))) return 1;
+    return thsp_tile_sumsq_f64(plan->nrow, y, tile_ss, stream);   // the same numbers from a pass over y
 }
 int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, int accumulate, thsp_stream_t stream)
 {

@@ -32,6 +32,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tree_sum.cuh"
 
 namespace thsp {
 
@@ -127,12 +128,15 @@ __global__ void xchg_reduce_kernel(uint64_t* ctrl, uint64_t iter, int world, dou
     const int r = threadIdx.x;
     const int par = (int)(iter & 1);
     double v = 0.0;
+    bool ok = true;
     if (r < world) {
-        spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
+        ok = spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
         v = __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r));
     }
     double tot = 0.0;
     for (int k = 0; k < world; ++k) tot = add_rn(tot, __shfl_sync(0xffffffffu, v, k));
+    // a peer that never published: poison the sum, so that the step cannot go on with stale partials unnoticed
+    if (!__all_sync(0xffffffffu, ok)) tot = __longlong_as_double(0x7ff8000000000000LL);
     if (r == 0) *sumsq_out = tot;
 }
 
@@ -165,10 +169,113 @@ __global__ void __launch_bounds__(kXThreads) xchg_scale_push_kernel(int64_t n, c
     if (dst.n == 0) return;
     if (remote) __threadfence_system();   // this thread's remote stores are visible before the ticket
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();           // ... and ordered before the ticket in the thread that takes it
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (last && threadIdx.x < 32) {
         if (threadIdx.x == 0) *ticket = 0;
+        __threadfence_system();
+        if ((int)threadIdx.x < dst.n) st_relaxed_sys(dst.ctrl[threadIdx.x] + kXHalo + rank, iter);
+    }
+}
+
+// ---- the whole vector half of a step in ONE kernel -----------------------------------------------------------------
+// Input: the per-tile sums of squares the SpMV left behind (csr_spmv.cu epilogue, tree_sum.cuh).  All CTAs are resident
+// at once (cooperative launch), because they wait for each other and for the peers:
+//   1. CTAs reduce blocks of 4096 tile partials with the index-bit tree; the last one to finish completes the tree over
+//      the block results and stores the rank's partial + flag into every rank's control block (lane p -> rank p);
+//   2. a warp of EVERY CTA waits for the flags of all ranks (lane r on rank r) and combines the partials with the same
+//      tree over rank numbers: same bits on every rank and - for aligned row blocks - as on one GPU;
+//   3. x_own = y / sqrt(sum) into the local replica and, for the ranges other ranks read, into their replicas; the last
+//      CTA to finish raises the "pieces from <rank>" flags.
+// A peer that never shows up (~15 s) poisons the sum with NaN and no flag is raised: the failure is loud, not silent.
+__global__ void __launch_bounds__(kXThreads) xchg_norm_scale_push_kernel(int ntiles, const double* __restrict__ tile_ss, double* part,
+                                                                         unsigned* __restrict__ tickets, int64_t n,
+                                                                         const double* __restrict__ y, uint64_t iter, int world, int rank,
+                                                                         XPeers peers, double* __restrict__ x_local, int64_t offset,
+                                                                         XDests dst, double* __restrict__ sumsq_out)
+{
+    __shared__ bool last;
+    __shared__ double s_tot;
+    static_assert(kXThreads == kTreeThreads, "block_tree_sum is written for this CTA size");
+    const int nb = (ntiles + kTreeBlock - 1) / kTreeBlock;
+    double* part_b = part + nb;
+    const int par = (int)(iter & 1);
+    // ---- 1. this rank's partial
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const double r = block_tree_sum(tile_ss + (size_t)b * kTreeBlock, min(kTreeBlock, ntiles - b * kTreeBlock));
+        if (threadIdx.x == 0) part[b] = r;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(tickets, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        const double mine = nb > 0 ? block_tree_finish(part, nb, part, part_b) : 0.0;
+        if (threadIdx.x < 32) {
+            const int p = threadIdx.x;
+            if (p == 0) tickets[0] = 0;
+            if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPart + par * kXMaxRanks + rank, (uint64_t)__double_as_longlong(mine));
+            __threadfence_system();
+            if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPartFlag + par * kXMaxRanks + rank, iter);
+        }
+    }
+    // ---- 2. everybody's partials, combined by the tree over rank numbers
+    if (threadIdx.x < 32) {
+        uint64_t* ctrl = peers.ctrl[rank];
+        const int r = threadIdx.x;
+        double v = 0.0;
+        bool ok = true;
+        if (r < world) {
+            ok = spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
+            v = __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r));
+        }
+#pragma unroll
+        for (int o = 1; o < kXMaxRanks; o <<= 1) v = add_rn(v, __shfl_down_sync(0xffffffffu, v, o));   // lanes >= world hold +0.0
+        if (!__all_sync(0xffffffffu, ok)) v = __longlong_as_double(0x7ff8000000000000LL);
+        if (r == 0) s_tot = v;
+    }
+    __syncthreads();
+    const double tot = s_tot;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sumsq_out = tot;
+    if (tot != tot) return;   // poisoned: leave x alone and raise nothing
+    // ---- 3. normalise, store locally and into the neighbours' replicas
+    const double inv = 1.0 / sqrt(tot);
+    const int64_t stride = (int64_t)gridDim.x * kXThreads;
+    bool remote = false;
+    constexpr int U = 4;   // independent loads in flight per thread
+    for (int64_t i0 = (int64_t)blockIdx.x * kXThreads + threadIdx.x; i0 < n; i0 += U * stride) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = i0 + u * stride < n ? ld_stream(y + i0 + u * stride) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n) break;
+            const double w = mul_rn(inv, v[u]);   // vec_axpby's beta == 0 branch: w = alpha * x
+            const int64_t g = offset + i;
+            x_local[g] = w;
+            for (int d = 0; d < dst.n; ++d)
+                if (g >= dst.lo[d] && g < dst.hi[d]) {
+                    dst.x[d][g] = w;
+                    remote = true;
+                }
+        }
+    }
+    if (dst.n == 0) return;
+    if (remote) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(tickets + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        if (threadIdx.x == 0) tickets[1] = 0;
         __threadfence_system();
         if ((int)threadIdx.x < dst.n) st_relaxed_sys(dst.ctrl[threadIdx.x] + kXHalo + rank, iter);
     }
@@ -231,6 +338,46 @@ int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter, int worl
     int grid = (int)std::min<int64_t>(sm_count() * 8, std::max<int64_t>(1, (n + kXThreads * 4 - 1) / (kXThreads * 4)));
     unsigned* ticket = static_cast<unsigned*>(work) + 1;
     xchg_scale_push_kernel<<<grid, kXThreads, 0, s>>>(n, y, ticket, iter, rank, x_local, offset, d, sumsq_out);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_xchg_norm_scale_push_f64(int64_t n, const double* y, const double* tile_ss, uint64_t iter, int world, int rank,
+                                  void* const* peer_ctrl, void* work, double* x_local, int64_t offset, int ndest,
+                                  double* const* dest_x, void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi,
+                                  double* sumsq_out, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    THSP_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "bad world / rank");
+    THSP_REQUIRE(ndest >= 0 && ndest < kXMaxRanks, "too many destinations");
+    THSP_REQUIRE(sumsq_out != nullptr && tile_ss != nullptr, "tile_ss / sumsq_out missing");
+    const int64_t ntiles64 = (n + 31) / 32;
+    THSP_REQUIRE(ntiles64 <= (int64_t)4095 * kTreeBlock, "slice too long for the work buffer");
+    XPeers pe;
+    for (int p = 0; p < kXMaxRanks; ++p) pe.ctrl[p] = p < world ? static_cast<uint64_t*>(peer_ctrl[p]) : nullptr;
+    XDests d;
+    d.n = ndest;
+    for (int k = 0; k < kXMaxRanks; ++k) {
+        d.x[k] = k < ndest ? dest_x[k] : nullptr;
+        d.ctrl[k] = k < ndest ? static_cast<uint64_t*>(dest_ctrl[k]) : nullptr;
+        d.lo[k] = k < ndest ? dest_lo[k] : 0;
+        d.hi[k] = k < ndest ? dest_hi[k] : 0;
+    }
+    // all CTAs must be resident together: they wait for each other's block results and for the peers
+    static int per_sm[16] = {};
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    if (!per_sm[dev & 15]) {
+        int k = 0;
+        THSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, xchg_norm_scale_push_kernel, kXThreads, 0));
+        per_sm[dev & 15] = std::max(1, std::min(k, 4));
+    }
+    int grid = (int)std::min<int64_t>((int64_t)sm_count() * per_sm[dev & 15], std::max<int64_t>(1, (n + kXThreads * 4 - 1) / (kXThreads * 4)));
+    int ntiles = (int)ntiles64;
+    unsigned* tickets = static_cast<unsigned*>(work);
+    double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
+    void* args[] = {&ntiles, (void*)&tile_ss, &part, &tickets, &n, (void*)&y, &iter, &world, &rank, &pe, &x_local, &offset, &d, &sumsq_out};
+    THSP_CUDA(cudaLaunchCooperativeKernel((const void*)xchg_norm_scale_push_kernel, dim3(grid), dim3(kXThreads), args, 0, as_stream(stream)));
     THSP_LAUNCH_CHECK();
     return 0;
 }

@@ -199,44 +199,103 @@ __global__ void __launch_bounds__(1024) coo_probe_kernel(int nrow, int nnz, cons
 }
 
 // ============================================================================ CSC ==========
-// Column scatter with shared-memory-staged partial sums.  A CTA owns kCscCols consecutive
-// columns, i.e. one contiguous run of (row_ind, val) entries, which it streams with coalesced
-// loads.  The column of each entry comes from a binary search in the CTA's slice of col_ptr
-// (kept in shared memory).  Partial sums for rows inside a dense window of kCscWin rows centred
-// on the CTA's columns (where banded / stencil matrices put most of their entries) are
-// accumulated with shared-memory atomics and flushed once with one global atomic per touched
-// row; rows outside the window go straight to global atomics.
-// Order: unspecified (atomics), like the reference's `omp atomic` scatter (:88-91).
-static constexpr int kCscCols = 256;
+// Column scatter with shared-memory-staged partial sums, ENTRY-balanced: a CTA owns kCscChunk consecutive entries,
+// whatever columns they belong to (a hub column of a power-law matrix is spread over many CTAs; with 256 columns per
+// CTA, as in round 1, one CTA was left with 10^6 entries of the R-MAT matrix: 13.6 ms).
+//   0. csc_partition_kernel: the column that holds the first entry of every chunk (binary search in col_ptr).
+//   1. the CTA loads the col_ptr slice of its columns into shared memory (up to kCscMaxCols; past that, lanes search
+//      global memory);
+//   2. lane l owns 16 CONSECUTIVE entries: 256-bit loads of row_ind and val (one whole sector per request, L2
+//      evict-first), one binary search for the column of its first entry, then it walks: the column advances when the
+//      entry index reaches the next column pointer; x[column] is read once per column, not per entry;
+//   3. products for rows inside a window of kCscWin rows centred on the CTA's columns (where banded / stencil matrices
+//      put a third or more of their entries) are added in shared memory and flushed with one red.global per touched
+//      row; all others go to y with red.global.add.f64 directly.
+// Order: unspecified (atomics), like the reference's `omp atomic` scatter (src/mat_vec.cpp:88-91).
+static constexpr int kCscIPT = 16;                       // entries owned by a lane
+static constexpr int kCscChunk = 256 * kCscIPT;          // entries per CTA
+static constexpr int kCscMaxCols = 4096;                 // col_ptr slice kept in shared memory
 static constexpr int kCscWin = 2048;
 
-__global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, const int* __restrict__ col_ptr,
-                                                  const int* __restrict__ row, const double* __restrict__ val,
-                                                  const double* __restrict__ x, double* __restrict__ y)
+__global__ void __launch_bounds__(256) csc_partition_kernel(int ncol, int nnz, const int* __restrict__ col_ptr, int nchunks,
+                                                            int* __restrict__ part)
 {
-    __shared__ int s_cp[kCscCols + 1];
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t > nchunks) return;
+    const int64_t e = min((int64_t)t * kCscChunk, (int64_t)nnz);
+    // last column c with col_ptr[c] <= e (empty columns at e: the last of them, which is where the entry lives)
+    int lo = 0, hi = ncol;   // col_ptr[lo] <= e < col_ptr[hi] (col_ptr[ncol] = nnz; e == nnz -> ncol)
+    if (e >= nnz) {
+        part[t] = ncol;
+        return;
+    }
+    while (hi - lo > 1) {
+        const int mid = (int)(((int64_t)lo + hi) >> 1);
+        if (__ldg(col_ptr + mid) <= e) lo = mid; else hi = mid;
+    }
+    part[t] = lo;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, const int* __restrict__ col_ptr,
+                                                  const int* __restrict__ row, const double* __restrict__ val,
+                                                  const double* __restrict__ x, double* __restrict__ y,
+                                                  const int* __restrict__ part)
+{
+    __shared__ int s_cp[kCscMaxCols + 2];
     __shared__ double s_win[kCscWin];
-    const int c0 = blockIdx.x * kCscCols;
-    const int nc = min(kCscCols, ncol - c0);
-    for (int i = threadIdx.x; i <= nc; i += 256) s_cp[i] = __ldg(col_ptr + c0 + i);
+    const int e0 = blockIdx.x * kCscChunk;
+    const int e1 = min(e0 + kCscChunk, nnz);
+    const int c_lo = __ldg(part + blockIdx.x);
+    const int c_hi = min(__ldg(part + blockIdx.x + 1), ncol - 1);   // column of the first entry of the next chunk
+    const int span = c_hi - c_lo + 1;                               // columns that may hold entries of this chunk
+    const bool in_smem = span <= kCscMaxCols;
+    if (in_smem)
+        for (int i = threadIdx.x; i <= span; i += 256) s_cp[i] = __ldg(col_ptr + c_lo + i);
     for (int i = threadIdx.x; i < kCscWin; i += 256) s_win[i] = 0.0;
     __syncthreads();
-    const int e0 = s_cp[0], e1 = s_cp[nc];
-    const uint64_t pol = policy_evict_first();   // row_ind / val are read once: leave L2 to y
-    // window of rows around the diagonal block of these columns
-    int w0 = c0 + nc / 2 - kCscWin / 2;
+    int w0 = c_lo + span / 2 - kCscWin / 2;
     w0 = max(0, min(w0, nrow - kCscWin));
-    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
-        int lo = 0, hi = nc;  // s_cp[lo] <= e < s_cp[hi]
+    const uint64_t pol = policy_evict_first();   // row_ind / val are read once: leave L2 to y
+    const int e = e0 + threadIdx.x * kCscIPT;
+    if (e < e1) {
+        const int n = min(kCscIPT, e1 - e);
+        int rr[kCscIPT];
+        load_block8<kVec>(row + e, n, rr, pol);
+        load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
+        // column of the lane's first entry: last c in [c_lo, c_hi] with col_ptr[c] <= e
+        int lo = 0, hi = span;   // cp[lo] <= e < cp[hi]
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (s_cp[mid] <= e) lo = mid; else hi = mid;
+            const int v = in_smem ? s_cp[mid] : __ldg(col_ptr + c_lo + mid);
+            if (v <= e) lo = mid; else hi = mid;
         }
-        const int r = ld_stream_ef(row + e, pol);
-        const double p = mul_rn(ld_stream_ef(val + e, pol), ld_gather(x + c0 + lo));
-        const int w = r - w0;
-        if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
-        else atomicAdd(y + r, p);
+        int c = lo;
+        int next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
+        double xc = ld_gather(x + c_lo + c);
+#pragma unroll
+        for (int h = 0; h < kCscIPT; h += 8) {
+            double vv[8];
+            load_block8<kVec>(val + e + h, n - h, vv, pol);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (h + k < n) {
+                    const int g = e + h + k;
+                    if (g >= next) {   // rare: walk over the column boundary (and any empty columns)
+                        do {
+                            ++c;
+                            next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
+                        } while (g >= next);
+                        xc = ld_gather(x + c_lo + c);
+                    }
+                    const double p = mul_rn(vv[k], xc);
+                    const int r = rr[h + k];
+                    const int w = r - w0;
+                    if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
+                    else atomicAdd(y + r, p);
+                }
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kCscWin; i += 256) {
@@ -464,10 +523,17 @@ int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row
 int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int* row_ind, const double* val,
                       const double* x, double* y, thsp_stream_t stream)
 {
-    (void)nnz;
     if (ensure_device()) return 1;
-    if (ncol <= 0 || nrow <= 0) return 0;
-    csc_kernel<<<div_up(ncol, kCscCols), 256, 0, as_stream(stream)>>>(nrow, ncol, col_ptr, row_ind, val, x, y);
+    if (ncol <= 0 || nrow <= 0 || nnz <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const int nchunks = div_up(nnz, kCscChunk);
+    int* part = static_cast<int*>(scratch(sizeof(int) * ((size_t)nchunks + 1), 2));
+    if (!part) return 1;
+    csc_partition_kernel<<<div_up(nchunks + 1, 256), 256, 0, s>>>(ncol, nnz, col_ptr, nchunks, part);
+    THSP_LAUNCH_CHECK();
+    const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads of whole sectors
+    if (vec) csc_kernel<true><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part);
+    else csc_kernel<false><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part);
     THSP_LAUNCH_CHECK();
     return 0;
 }

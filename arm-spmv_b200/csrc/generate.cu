@@ -4,6 +4,8 @@
 // 512^3 does not fit the reference's int32 structs at all), so matrices are generated straight
 // into device memory.  oracle/oracle.c holds CPU twins that produce identical arrays, which is
 // how parity tests get the same matrix on both sides.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace thsp {
@@ -175,6 +177,18 @@ __global__ void __launch_bounds__(256) flush_kernel(size_t n16, int4* __restrict
     const size_t stride = (size_t)gridDim.x * 256;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += stride) p[i] = make_int4(tag, tag, tag, tag);
 }
+// Order-independent 64-bit fingerprint of a piece of a vector: sum over i of mix64(bits(v_i) ^ mix64(first + i)) modulo
+// 2^64.  Pieces of one vector add up to the fingerprint of the whole, whoever holds them.
+__global__ void __launch_bounds__(256) hash_kernel(int64_t n, const double* __restrict__ v, uint64_t first, unsigned long long* __restrict__ out)
+{
+    unsigned long long h = 0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+        h += mix64((uint64_t)__double_as_longlong(v[i]) ^ mix64(first + (uint64_t)i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+}
 __global__ void __launch_bounds__(256) slice_row_ptr_kernel(const int* __restrict__ rp, int start, int count, int* __restrict__ sub)
 {
     const int j = blockIdx.x * 256 + threadIdx.x;
@@ -267,6 +281,22 @@ int thsp_f64_to_f32(int64_t n, const double* src, float* dst, thsp_stream_t stre
     THSP_LAUNCH_CHECK();
     return 0;
 }
+int thsp_hash_f64(int64_t n, const double* v, uint64_t first_index, uint64_t* hash_host, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    cudaStream_t s = as_stream(stream);
+    unsigned long long* d = static_cast<unsigned long long*>(scratch(sizeof(unsigned long long), 1));
+    if (!d) return 1;
+    THSP_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s));
+    if (n > 0) {
+        hash_kernel<<<(int)std::min<int64_t>((int64_t)sm_count() * 8, (n + 255) / 256), 256, 0, s>>>(n, v, first_index, d);
+        THSP_LAUNCH_CHECK();
+    }
+    THSP_CUDA(cudaMemcpyAsync(hash_host, d, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int thsp_flush_l2(void* scratch_buf, size_t bytes, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;

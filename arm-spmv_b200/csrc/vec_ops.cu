@@ -6,7 +6,10 @@
 // so their outputs are bit-identical to the reference.  All are pure streaming kernels
 // (HBM-bound): 256-thread CTAs, 4 independent elements in flight per thread, grid sized to a
 // multiple of the SM count.
+#include <algorithm>
+
 #include "common.cuh"
+#include "tree_sum.cuh"
 
 namespace thsp {
 
@@ -135,6 +138,33 @@ __global__ void __launch_bounds__(kEwThreads) scale_broadcast_kernel(int64_t n, 
     }
 }
 
+// ---- canonical sum of squares (tree_sum.cuh): tile partials, then the index-bit tree ----------------------------
+// tile_ss[t] = butterfly sum of y_i^2 over rows [32 t, 32 t + 32); a warp per tile.  The CSR stream kernel writes the
+// same numbers from its epilogue (csr_spmv.cu); this kernel serves the other kernels and other callers.
+__global__ void __launch_bounds__(256) tile_sumsq_kernel(int64_t n, const double* __restrict__ y, double* __restrict__ tile_ss)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + 31) >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, GW = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t t = gw; t < ntiles; t += GW) {
+        const int64_t i = t * 32 + lane;
+        const double v = i < n ? ld_stream(y + i) : 0.0;
+        const double q = warp_butterfly_sum(mul_rn(v, v));
+        if (lane == 0) tile_ss[t] = q;
+    }
+}
+__global__ void __launch_bounds__(kTreeThreads) tree_blocks_kernel(int64_t m, const double* __restrict__ vals, double* __restrict__ out)
+{
+    const int64_t b0 = (int64_t)blockIdx.x * kTreeBlock;
+    const double r = block_tree_sum(vals + b0, (int)min((int64_t)kTreeBlock, m - b0));
+    if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(kTreeThreads) tree_finish_kernel(int m, double* a, double* b, double* __restrict__ out)
+{
+    const double r = block_tree_finish(a, m, a, b);
+    if (threadIdx.x == 0) *out = r;
+}
+
 // diag[i] = sum of the entries (i, i) of a CSR matrix (0 when the row has none), one thread per row.
 __global__ void __launch_bounds__(256) csr_diagonal_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
                                                            const double* __restrict__ va, double* __restrict__ diag)
@@ -190,6 +220,42 @@ int thsp_sumsq_dev_f64(int64_t n, const double* y, double* out_dev, thsp_stream_
 {
     if (ensure_device()) return 1;
     return dot_to_device(n, y, y, out_dev, as_stream(stream));
+}
+
+int thsp_tile_sumsq_f64(int64_t n, const double* y, double* tile_ss, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    if (n <= 0) return 0;
+    const int64_t ntiles = (n + 31) / 32;
+    const int grid = (int)std::min<int64_t>((int64_t)sm_count() * 8, (ntiles + 7) / 8);
+    tile_sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, y, tile_ss);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_tree_sum_f64(int64_t m, const double* vals, double* out_dev, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    cudaStream_t s = as_stream(stream);
+    if (m <= 0) {
+        THSP_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+        return 0;
+    }
+    const int64_t nb = (m + kTreeBlock - 1) / kTreeBlock;
+    THSP_REQUIRE(nb <= (int64_t)1 << 30, "too many values");
+    if (nb == 1) {
+        tree_blocks_kernel<<<1, kTreeThreads, 0, s>>>(m, vals, out_dev);
+        THSP_LAUNCH_CHECK();
+        return 0;
+    }
+    const int64_t nb2 = (nb + kTreeBlock - 1) / kTreeBlock;
+    double* a = static_cast<double*>(scratch(sizeof(double) * (size_t)(nb + nb2 + 2), 0));
+    if (!a) return 1;
+    tree_blocks_kernel<<<(int)nb, kTreeThreads, 0, s>>>(m, vals, a);
+    THSP_LAUNCH_CHECK();
+    tree_finish_kernel<<<1, kTreeThreads, 0, s>>>((int)nb, a, a + nb, out_dev);
+    THSP_LAUNCH_CHECK();
+    return 0;
 }
 
 int thsp_axpby_f64(int64_t n, double alpha, const double* x, double beta, const double* y, double* w, thsp_stream_t stream)

@@ -24,8 +24,8 @@ x refresh modes
              only the parts of that range owned by other ranks are pulled.
   xchg       the same footprint, but nothing is pulled and no collective is called: the kernel that
              normalises y stores the pieces other ranks read straight into their replicas and raises
-             a flag; the sum of squares travels the same way (csrc/exchange.cu).  One stream, five
-             kernels per step, no host synchronisation.
+             a flag; the sum of squares travels the same way (csrc/exchange.cu).  One stream, four
+             kernels per step (interior rows, wait, boundary rows, everything else), no host synchronisation.
 With `overlap`, rows whose columns all fall inside the own slice (interior) are multiplied while
 the refresh is still in flight; the boundary blocks wait for it.
 
@@ -58,27 +58,29 @@ def partition_rows(n: int, nparts: int, part: int) -> tuple[int, int]:
 def stencil_row_blocks(n: int, start: int, count: int, world: int, max_rows: int) -> list[tuple[int, int, bool]]:
     """Split rows [start, start+count) of the n^3 27-point stencil into (r0, r1, boundary) pieces.
     Boundary pieces are the first / last grid plane of the slab when another rank owns the
-    neighbouring plane; interior pieces are cut so that each holds < 2^31 entries."""
+    neighbouring plane; interior pieces are cut so that each holds < 2^31 entries.  Every piece starts a
+    multiple of 32 rows after `start`, so that the pieces' 32-row tiles are tiles of the whole slice (the
+    canonical sum of squares, csrc/tree_sum.cuh); boundary pieces are rounded outwards for that."""
     end = start + count
     plane = n * n
     reach = plane + n + 1            # furthest column offset of a row
+    up = lambda v: (v + 31) // 32 * 32
     pieces = []
-    lo, hi = start, end
+    lo, hi = 0, count                # relative to start
     if world > 1 and start > 0:
-        b = min(end, start + reach)
-        pieces.append((start, b, True))
+        b = min(count, up(reach))
+        pieces.append((start, start + b, True))
         lo = b
     tail = None
-    if world > 1 and end < n ** 3 and hi - reach > lo:
-        tail = (hi - reach, hi, True)
-        hi -= reach
-    elif world > 1 and end < n ** 3 and hi > lo:
-        tail = (lo, hi, True)
-        hi = lo
+    if world > 1 and end < n ** 3 and hi > lo:
+        t0 = max(lo, (hi - reach) // 32 * 32)
+        tail = (start + t0, end, True)
+        hi = t0
+    step = max(32, max_rows // 32 * 32)
     r = lo
     while r < hi:
-        e = min(hi, r + max_rows)
-        pieces.append((r, e, False))
+        e = min(hi, r + step)
+        pieces.append((start + r, start + e, False))
         r = e
     if tail:
         pieces.append(tail)
@@ -129,9 +131,22 @@ class CudaOps:
         self.check(self.lib.thsp_csc_spmv_f64(payload.nrow, payload.ncol, payload.nnz, self.ptr(payload.col_ptr), self.ptr(payload.row_ind),
                                               self.ptr(payload.values), self.ptr(x), self.ptr(y), self.stream()))
 
-    def spmv(self, payload, x, y):
-        """y = A_block x (overwrite: saves Fill(0) and the read of y)."""
-        self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
+    def spmv(self, payload, x, y, tile_ss=None):
+        """y = A_block x (overwrite: saves Fill(0) and the read of y); with tile_ss also the sum of squares of every
+        32-row tile of y, written by the SpMV's epilogue (thsp_csr_plan_spmv_sumsq_f64)."""
+        if tile_ss is None:
+            self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
+        else:
+            self.check(self.lib.thsp_csr_plan_spmv_sumsq_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.ptr(tile_ss), self.stream()))
+
+    def tree_sum(self, vals, out):
+        """out[0] = the canonical (index-bit tree) sum of vals: tile partials of one rank, or the ranks' partials."""
+        self.check(self.lib.thsp_tree_sum_f64(C.c_int64(vals.numel()), self.ptr(vals), self.ptr(out), self.stream()))
+
+    def hash(self, v, first):
+        h = C.c_uint64(0)
+        self.check(self.lib.thsp_hash_f64(C.c_int64(v.numel()), self.ptr(v), C.c_uint64(first), C.byref(h), self.stream()))
+        return int(h.value)
 
     def reserve_sms(self, payload, reserve):
         """Run this block's persistent SpMV on (SMs - reserve) CTAs so that a collective launched on
@@ -189,6 +204,12 @@ class CudaOps:
                                                      C.c_void_p(self.ctrl_ptrs[self.xr]), self.ptr(self.work), self.ptr(x), C.c_int64(offset),
                                                      self.nd, self.d_x, self.d_ctrl, self.d_lo, self.d_hi, self.ptr(ss), self.stream()))
 
+    def norm_scale_push(self, y, tile_ss, it, x, offset, ss):
+        """reduce + publish + combine + normalise + push + flags in one kernel (thsp_xchg_norm_scale_push_f64)"""
+        self.check(self.lib.thsp_xchg_norm_scale_push_f64(C.c_int64(y.numel()), self.ptr(y), self.ptr(tile_ss), C.c_uint64(it), self.xw, self.xr,
+                                                          self.ctrl_arr, self.ptr(self.work), self.ptr(x), C.c_int64(offset), self.nd, self.d_x,
+                                                          self.d_ctrl, self.d_lo, self.d_hi, self.ptr(ss), self.stream()))
+
     def wait_halo(self, it, src_mask):
         if it > 0 and src_mask:
             self.check(self.lib.thsp_xchg_wait(C.c_void_p(self.ctrl_ptrs[self.xr]), C.c_uint64(it), C.c_uint(src_mask), self.stream()))
@@ -240,11 +261,15 @@ class PartitionedCSR:
         bnd = world > 1 and (lo < start or hi >= start + count)
         return PartitionedCSR(nrow, rank, world, start, count, [RowBlock(start, count, nnz, bnd, payload, lo, hi)])
 
-    def spmv(self, ops, x, y_local, boundary: bool | None = None):
+    def spmv(self, ops, x, y_local, boundary: bool | None = None, tile_ss=None):
         for b in self.blocks:
             if boundary is None or b.boundary == boundary:
                 off = b.row0 - self.start
-                ops.spmv(b.payload, x, y_local[off:off + b.nrow])
+                if tile_ss is None:
+                    ops.spmv(b.payload, x, y_local[off:off + b.nrow])
+                else:   # blocks start on tile boundaries of the slice (stencil_row_blocks, from_csr)
+                    assert off % 32 == 0
+                    ops.spmv(b.payload, x, y_local[off:off + b.nrow], tile_ss[off // 32:off // 32 + (b.nrow + 31) // 32])
 
     def needed_ranges(self) -> list[tuple[int, int, int]]:
         """(owner rank, lo, hi) pieces of x outside the own slice that the boundary blocks read."""
@@ -276,6 +301,10 @@ class PowerIteration:
                 ops.reserve_sms(b.payload, free)
         self.y = ops.empty(A.count)
         self.ss = ops.scalar()
+        # sum of squares in the canonical order (csrc/tree_sum.cuh): per-tile partials from the SpMV's epilogue,
+        # index-bit tree over the tiles, then over the ranks - the same bits on 1, 2, 4, 8 GPUs for aligned row blocks
+        self.tile_ss = ops.empty((A.count + 31) // 32)
+        self.rank_ss = ops.empty(self.world) if self.world > 1 else None
         self.symm = None
         if self.world > 1 and exchange in ("fused", "push", "cepush", "halo", "xchg") and hasattr(ops, "symmetric_x"):
             self.x = ops.symmetric_x(A.N)     # CPU test ops: plain memory, exchanges emulated over gloo
@@ -324,21 +353,22 @@ class PowerIteration:
         cur = torch.cuda.current_stream() if self.comm_stream is not None else None
         self._mark("start")
         if self.world > 1 and self.overlap:
-            A.spmv(ops, self.x, self.y, boundary=False)      # needs only the own slice of x
+            A.spmv(ops, self.x, self.y, boundary=False, tile_ss=self.tile_ss)      # needs only the own slice of x
             self._mark("interior rows")
             self._wait_refresh(cur)
             self._mark("wait for refresh")
-            A.spmv(ops, self.x, self.y, boundary=True)
+            A.spmv(ops, self.x, self.y, boundary=True, tile_ss=self.tile_ss)
             self._mark("boundary rows")
         else:
             self._wait_refresh(cur)
-            A.spmv(ops, self.x, self.y)
+            A.spmv(ops, self.x, self.y, tile_ss=self.tile_ss)
             self._mark("all rows")
-        ops.sumsq(self.y, self.ss)
+        ops.tree_sum(self.tile_ss, self.ss)
         self._mark("sum of squares")
         if self.world > 1:
-            dist.all_reduce(self.ss, group=self.group)        # 8 bytes
-            self._mark("all-reduce")
+            dist.all_gather_into_tensor(self.rank_ss, self.ss, group=self.group)        # 8 bytes per rank
+            ops.tree_sum(self.rank_ss, self.ss)
+            self._mark("all-gather of the partials")
         self._scale_and_refresh(cur)
         self._mark("scale (+ refresh launch)")
 
@@ -369,20 +399,18 @@ class PowerIteration:
         k = self.iter + 1
         self._mark("start")
         if self.overlap:
-            A.spmv(ops, self.x, self.y, boundary=False)
+            A.spmv(ops, self.x, self.y, boundary=False, tile_ss=self.tile_ss)
             self._mark("interior rows")
             ops.wait_halo(k - 1, self.src_mask)
             self._mark("wait for neighbours")
-            A.spmv(ops, self.x, self.y, boundary=True)
+            A.spmv(ops, self.x, self.y, boundary=True, tile_ss=self.tile_ss)
             self._mark("boundary rows")
         else:
             ops.wait_halo(k - 1, self.src_mask)
-            A.spmv(ops, self.x, self.y)
+            A.spmv(ops, self.x, self.y, tile_ss=self.tile_ss)
             self._mark("all rows")
-        ops.sumsq_publish(self.y, k)
-        self._mark("sum of squares + publish")
-        ops.scale_push(self.y, k, self.x, A.start, self.ss)
-        self._mark("reduce + scale + push")
+        ops.norm_scale_push(self.y, self.tile_ss, k, self.x, A.start, self.ss)
+        self._mark("tree + publish + combine + scale + push")
         self.iter = k
 
     def _wait_refresh(self, cur):
@@ -462,15 +490,20 @@ class PowerIteration:
             raise RuntimeError("flag-based exchange: a wait on a peer gave up (peer stalled or died)")
         return math.sqrt(float(self.ss.item()))
 
+    def y_hash(self) -> int:
+        """Order-independent fingerprint of this rank's rows of y at their global positions (thsp_hash_f64): the ranks'
+        values add up (mod 2^64) to the fingerprint of the whole vector on one GPU."""
+        return self.ops.hash(self.y, self.A.start)
+
     def bytes_per_step(self) -> int:
         """Algorithmic HBM bytes this rank moves per iteration: CSR stream + x once +
-        y write, then y read (sumsq), y read + x-slice write (scale)."""
+        y write (the sums of squares leave the SpMV's epilogue: y is not read for them), y read + x-slice write (scale)."""
         a = self.A
         rows = a.count
         lo = min((b.col_min for b in a.blocks), default=0)
         hi = max((b.col_max for b in a.blocks), default=-1)
         x_read = max(0, hi - lo + 1)   # the columns this rank's rows touch (own slab + halo), not all of x
-        return a.nnz_local * 12 + (rows + len(a.blocks)) * 4 + x_read * 8 + rows * 8 + rows * 8 + rows * 16
+        return a.nnz_local * 12 + (rows + len(a.blocks)) * 4 + x_read * 8 + rows * 8 + rows * 16
 
 
 def _all_gather_slices(x, own, n, world, equal_split, group):
@@ -617,8 +650,10 @@ def e2e_spmv_step_shared(it: "PowerIteration", x_host, yh):
                                                       C.c_void_p(it.y.data_ptr() + off * 8), 0, ops.stream()))
 
 
-def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler, with_e2e=True, reserve_sms=16):
-    """Time `steps` power-iteration steps per x-refresh mode (device events, max over ranks)."""
+def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler, with_e2e=True, reserve_sms=16, hash_parts=0):
+    """Time `steps` power-iteration steps per x-refresh mode (device events, max over ranks).  Every mode starts from
+    the same x0 and runs max(3, warmup) + steps steps, so `norm` and the fingerprint of y ("y_hash": this rank's rows;
+    "y_hash_parts": with hash_parts = G on one GPU, the rows each of G ranks would own) can be compared across GPU counts."""
     from .lib import launch_count
     ops = CudaOps(device)
     A = PartitionedCSR.stencil27(n, rank, world, ops)
@@ -655,7 +690,9 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
             dist.barrier()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         results[mode] = {"ms_per_step": float(ms.item()), "norm": it.norm(), "launches": int(launches), "clocks": clk.summary(),
-                         "bytes_per_step_rank": it.bytes_per_step()}
+                         "bytes_per_step_rank": it.bytes_per_step(), "y_hash": it.y_hash(), "steps_done": max(3, warmup) + steps}
+        if hash_parts:
+            results[mode]["y_hash_parts"] = [ops.hash(it.y[s0:s0 + c0], s0) for s0, c0 in (partition_rows(A.N, hash_parts, r) for r in range(hash_parts))]
         if os.environ.get("THSP_POWER_TRACE"):   # where the time goes, rank by rank (a separate, untimed run)
             it.trace_on()
             for _ in range(10):
@@ -740,8 +777,10 @@ MODE_NOTES = {
 }
 
 
-def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
-    """bench.py --gpus N under torchrun (one rank per GPU)."""
+def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler, extra=None):
+    """bench.py --gpus N under torchrun (one rank per GPU).  Returns non-zero when the N-GPU run does not reproduce the
+    one-GPU run (parity block of the line)."""
+    rc = 0
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -755,8 +794,26 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
         # 48 at 8 (profiles/r01_power_8gpu.txt)
         args.reserve_sms = 16 * max(1, int(math.log2(max(world, 2))))
     modes = [m for m in args.exchange.split(",") if m] if world > 1 else ["allgather"]
+    # The same workload on ONE GPU first (rank 0; 512^3 is 45 GB of 180): the denominator of the speed-up, and the norm
+    # and the fingerprints of y that the N-GPU run must reproduce bit for bit (same x0, same number of steps).
+    one = None
+    if world > 1 and not getattr(args, "no_one_gpu", False):
+        if rank == 0:
+            try:
+                A1, res1 = measure(n, 0, 1, device, args.steps, args.warmup, ["allgather"], True, ClockSampler, with_e2e=False, hash_parts=world)
+                one = res1["allgather"]
+                one["row_blocks"] = len(A1.blocks)
+                del A1, res1
+            except Exception as e:   # e.g. out of memory on a smaller GPU: the line then says so instead of a ratio
+                one = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+        dist.barrier()
     A, results = measure(n, rank, world, device, args.steps, args.warmup, modes, not args.no_overlap, ClockSampler,
                          reserve_sms=args.reserve_sms)
+    if world > 1:   # every rank's fingerprint of its rows of y, per mode, to rank 0
+        mine = {m: v.get("y_hash") for m, v in results.items() if isinstance(v, dict) and "y_hash" in v}
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
     if rank == 0:
         primary = next(m for m in modes if "ms_per_step" in results.get(m, {}))
         nnz_total = (3 * n - 2) ** 3
@@ -786,6 +843,30 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
                                      "norm": v["norm"]} if "ms_per_step" in v else v) for m, v in results.items()
                                 if m not in ("e2e", "e2e_allgather", "e2e_shared_x")},
         }
+        if one is not None and "ms_per_step" in one:
+            ms1 = one["ms_per_step"]
+            line["same_workload_1gpu"] = {"ms_per_step": round(ms1, 5), "gflops": round(flops / (ms1 * 1e-3) / 1e9, 2), "norm": one["norm"],
+                                          "steps_done": one["steps_done"], "row_blocks": one["row_blocks"],
+                                          "note": "the same power iteration on rank 0's GPU alone, timed in this run before the ranks start"}
+            line["speedup_vs_1gpu_same_workload"] = round(ms1 / ms, 4)
+            line["efficiency_same_workload"] = round(ms1 / ms / world, 4)
+            for m, v in line["x_refresh_modes"].items():
+                if "ms_per_step" in v:
+                    v["speedup_vs_1gpu_same_workload"] = round(ms1 / v["ms_per_step"], 4)
+            # parity across GPU counts: the canonical sum of squares (csrc/tree_sum.cuh) makes the whole loop reproducible
+            par = {"steps_compared_after": one["steps_done"]}
+            for m in modes:
+                v = results.get(m, {})
+                if "norm" not in v:
+                    continue
+                hashes = [h.get(m) for h in allh]
+                par[m] = {"norm_bits_equal_1gpu": bool(v["norm"] == one["norm"]),
+                          "norm_rel_diff": abs(v["norm"] - one["norm"]) / abs(one["norm"]),
+                          "y_hash_equal_1gpu": bool(hashes == one["y_hash_parts"]),
+                          "ranks_with_equal_y": int(sum(1 for a, b in zip(hashes, one["y_hash_parts"]) if a == b))}
+            line["parity"] = par
+        elif one is not None:
+            line["same_workload_1gpu"] = one
         for k2 in ("e2e_allgather", "e2e_shared_x"):   # the e2e variant that was not kept as the headline, for comparison
             v = results.get(k2)
             if v and "ms_per_step" in v:
@@ -793,7 +874,14 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler):
                             "h2d_bytes_per_step": v["h2d_bytes_per_step"], "d2h_bytes_per_step": v["d2h_bytes_per_step"], "call": v.get("call", "")}
             elif v:
                 line[k2] = v
+        if extra:
+            line.update(extra)
         print(json.dumps(line), flush=True)
+        par = line.get("parity", {}).get(primary)
+        if par and not (par["norm_rel_diff"] <= 1e-12):
+            print(f"bench.py: the {world}-GPU norm differs from the one-GPU norm: {par}", flush=True)
+            rc = 1
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return rc

@@ -118,12 +118,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_arm(n, reps, warm=1, iterated=False):
+def ref_checker():
+    """(checker, kind): the unmodified reference (oracle/_ref/libref.so) with all host threads - its CSR / ELL / DIA
+    loops give every row to one thread, so the bits do not depend on the thread count - else the C restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    try:
+        R = pyoracle.Ref()
+        R.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        return R, "reference"
+    except (FileNotFoundError, OSError):
+        return pyoracle.Oracle(), "port"
+
+
+def cpu_reference_arm(n, reps, warm=1, iterated=False, want_y=None):
     """The reference's CPU CSR SpMV (main.cpp:54-61 protocol) on an n^3 27-point stencil - or, with
     `iterated`, the power-iteration step composed from the reference's own calls (Fill, CSRMatrixMatVector,
     vec_dot, vec_axpby: SURVEY.md 3.5), which is what the N > 1 arm measures.
     Returns (gflops, seconds_per_call, kind, cores, sample, tuned) - `tuned` describes the same measurement with
-    the reference rebuilt at -O3 -march=x86-64-v3 (None when that library or the CPU features are missing)."""
+    the reference rebuilt at -O3 -march=x86-64-v3 (None when that library or the CPU features are missing).
+    `want_y` (a dict) receives the parity material of the same matrix: "y" = 0 + A x computed by the same checker,
+    "x" and the matrix "arrays", so that the caller can show the GPU multiplied the same matrix."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
@@ -133,6 +149,9 @@ def cpu_reference_arm(n, reps, warm=1, iterated=False):
     rp, ci, va = O.gen_stencil27_csr(n)
     N = n ** 3
     x = O.gen_vector(N, 11)
+    if want_y is not None:
+        want_y["x"] = x
+        want_y["arrays"] = (rp, ci, va)
     what = "power-iteration steps (y=0; y+=Ax; sqrt(dot); axpby)" if iterated else "back-to-back y+=Ax"
     try:
         R = pyoracle.Ref()
@@ -158,6 +177,9 @@ def cpu_reference_arm(n, reps, warm=1, iterated=False):
                 best = (d, t)
         cores = best[1]
         R.set_threads(cores)
+        if want_y is not None:
+            want_y["y"] = R.csr_spmv(N, N, rp, ci, va, x, np.zeros(N))
+            want_y["kind"] = "reference"
         for _ in range(warm):
             run(1)
         dt = run(reps)
@@ -173,6 +195,9 @@ def cpu_reference_arm(n, reps, warm=1, iterated=False):
             tuned = None
     except (FileNotFoundError, OSError):
         y = np.zeros(N)
+        if want_y is not None:
+            want_y["y"] = O.csr_spmv(N, N, rp, ci, va, x, np.zeros(N))
+            want_y["kind"] = "port"
         t0 = time.perf_counter()
         k = max(1, reps // 4)
         for _ in range(k):
@@ -214,6 +239,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------
 def run_single(args):
+    import numpy as np
     import torch
 
     import arm_spmv_b200 as pkg
@@ -285,6 +311,13 @@ def run_single(args):
     check(lib.thsp_csr_plan_spmv_f64(plan, ptr(x.values), ptr(yd), 0, stream))
     torch.cuda.synchronize()
     assert torch.equal(yd.cpu(), yh), "host-buffer path and device path disagree"
+    # ---- parity material (compared with the reference's own CSRMatrixMatVector further down, where the CPU arm runs)
+    parity = {}
+    do_parity = not args.no_cpu and args.cpu_grid == n
+    if do_parity:
+        y_dev_np = yd.cpu().numpy()          # 0 + A x by the kernel that was timed
+        y_host_np = yh.numpy().copy()        # the same through the host-buffer call
+        gpu_arrays = (A.row_ptr.cpu().numpy(), A.col_ind.cpu().numpy(), A.values.cpu().numpy(), x.values.cpu().numpy())
 
     # ---- ELL on the same matrix (configs[1] is "ELL vs CSR")
     extra = {}
@@ -307,6 +340,14 @@ def run_single(args):
         extra["ell"] = {"ms_per_step": round(ell_ms, 4), "gflops": round(2.0 * nnz / (ell_ms * 1e-3) / 1e9, 2),
                         "achieved_gbs": round(ell_bytes / (ell_ms * 1e-3) / 1e9, 1),
                         "frac": round(ell_bytes / (ell_ms * 1e-3) / 1e9 / peak, 4)}
+        if do_parity:
+            chk, _ = ref_checker()
+            ye.Fill(0.0)
+            H.ELLMatrixMatVector(E, x, ye)
+            torch.cuda.synchronize()
+            want = chk.ell_spmv(N, N, 27, E.col_ind.cpu().numpy(), E.values.cpu().numpy(), gpu_arrays[3], np.zeros(N))
+            parity["ell_bits"] = bool(ye.values.cpu().numpy().tobytes() == want.tobytes())
+            del want
         del E, ye
         # DIA: no index stream at all (8 B per entry) - the format with the highest roofline on a stencil
         Bc = H.CSRMatrix(nrow=N, ncol=N, row_ptr=A.row_ptr, col_ind=A.col_ind, values=A.values)
@@ -326,6 +367,13 @@ def run_single(args):
         dia_bytes = N * Dm.ndiags * 8 + Dm.ndiags * 4 + N * 8 + 2 * N * 8
         extra["dia"] = {"ms_per_step": round(dia_ms, 4), "gflops": round(2.0 * nnz / (dia_ms * 1e-3) / 1e9, 2), "ndiags": Dm.ndiags,
                         "achieved_gbs": round(dia_bytes / (dia_ms * 1e-3) / 1e9, 1), "frac": round(dia_bytes / (dia_ms * 1e-3) / 1e9 / peak, 4)}
+        if do_parity:
+            yd2.Fill(0.0)
+            H.DIAMatrixMatVector(Dm, x, yd2)
+            torch.cuda.synchronize()
+            want = chk.dia_spmv(N, N, Dm.offsets.cpu().numpy(), Dm.values.cpu().numpy(), gpu_arrays[3], np.zeros(N))
+            parity["dia_bits"] = bool(yd2.values.cpu().numpy().tobytes() == want.tobytes())
+            del want
         del Dm, yd2, Bc
 
     # ---- the iterated loop (power iteration) on one GPU: the denominator of the multi-GPU runs
@@ -335,22 +383,35 @@ def run_single(args):
         del A, x, y, yd, xh, yh
         torch.cuda.empty_cache()
         g = args.iterated_grid
-        Ap, res = power.measure(g, 0, 1, torch.device("cuda", 0), min(args.steps, 20), 3, ["allgather"], True, ClockSampler, with_e2e=False)
+        # same warm-up and step count as the N > 1 runs use: their norm and fingerprints of y must equal these bit for bit
+        Ap, res = power.measure(g, 0, 1, torch.device("cuda", 0), args.steps, args.warmup, ["allgather"], True, ClockSampler, with_e2e=False)
         r = res["allgather"]
         nnz_g = (3 * g - 2) ** 3
         extra["iterated"] = {"workload": f"power iteration, 27-point stencil {g}^3 ({nnz_g} nnz, {len(Ap.blocks)} row blocks of < 2^31 entries), 1 GPU",
                              "ms_per_step": round(r["ms_per_step"], 4), "gflops": round(2.0 * nnz_g / (r["ms_per_step"] * 1e-3) / 1e9, 2),
                              "achieved_gbs": round(r["bytes_per_step_rank"] / (r["ms_per_step"] * 1e-3) / 1e9, 1),
-                             "frac": round(r["bytes_per_step_rank"] / (r["ms_per_step"] * 1e-3) / 1e9 / peak, 4), "norm": r["norm"]}
+                             "frac": round(r["bytes_per_step_rank"] / (r["ms_per_step"] * 1e-3) / 1e9 / peak, 4), "norm": r["norm"],
+                             "steps_done": r["steps_done"], "y_hash": r["y_hash"]}
         del Ap
         torch.cuda.empty_cache()
 
     cpu = None
     if not args.no_cpu:
-        gf, dt, kind, cores, sample, tuned = cpu_reference_arm(args.cpu_grid, args.cpu_reps)
+        ref = {} if do_parity else None
+        gf, dt, kind, cores, sample, tuned = cpu_reference_arm(args.cpu_grid, args.cpu_reps, want_y=ref)
         cpu = {"value": round(gf, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         if tuned:
             cpu["rebuilt_o3"] = tuned
+        if do_parity:
+            # the GPU multiplied the matrix and the vector the reference multiplied (device generators vs the oracle's CPU
+            # twins, byte for byte), and y = 0 + A x has the reference's bits - through the device call and the host-buffer call
+            parity["inputs_bits"] = bool(all(g.tobytes() == h.tobytes() for g, h in zip(gpu_arrays, ref["arrays"] + (ref["x"],))))
+            parity["csr_bits"] = bool(y_dev_np.tobytes() == ref["y"].tobytes())
+            parity["csr_host_buffer_bits"] = bool(y_host_np.tobytes() == ref["y"].tobytes())
+            parity["checker"] = ("the reference's own CSRMatrixMatVector / ELLMatrixMatVector / DIAMatrixMatVector (oracle/_ref/libref.so)"
+                                 if ref["kind"] == "reference" else "oracle/oracle.c (libref.so absent)")
+            parity["what"] = f"y = 0 + A x on the {n}^3 stencil, x = gen_vector(seed 11), all {N} rows compared byte for byte"
+            del gpu_arrays, ref
 
     line = {
         "metric": METRIC, "value": round(gflops, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -371,13 +432,103 @@ def run_single(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if parity:
+        line["parity"] = parity
     line.update(extra)
     print(json.dumps(line), flush=True)
+    bad = [k for k, v in parity.items() if k.endswith("_bits") and not v]
+    if bad:
+        print(f"bench.py: parity FAILED against the reference: {bad}", file=sys.stderr, flush=True)
+        sys.exit(1)
+
+
+def preflight_multi(rank, world, device):
+    """Before the timed N-GPU runs: the two partitioned paths that the power iteration does not exercise, on a small matrix,
+    against the CPU checker (oracle/ - checker use only).  (1) power.ColumnPartitionedCSC: CSCMatrixMatVectorNuma's column
+    blocks (src/mat_vec.cpp:299-366) + the reduce-scatter of the private y's the reference leaves out; (2) the C++
+    *MatVectorNuma entry points with G = N GPUs in one process (bin/api_check on a committed fixture, rank 0 only; the
+    other ranks wait).  Returns a dict for the JSON line; a failure is reported there and makes bench.py exit non-zero."""
+    import subprocess
+    import tempfile
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from arm_spmv_b200 import host as H, power
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    O = pyoracle.Oracle()
+    out = {}
+    # ---- (1) column-partitioned CSC
+    n, nnz = 6000, 90000
+    ri, ci, va = O.gen_uniform_coo(n, n, nnz, 47)
+    cp, ro, vo = O.coo2csc(n, n, ri, ci, va)
+    xh = O.gen_vector(n, 5) - 0.5
+    want = O.coo_spmv(n, n, ri, ci, va, xh, np.zeros(n))
+    scale = np.bincount(ri, weights=np.abs(va * xh[ci]), minlength=n)
+    ops = power.CudaOps(device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    P = power.ColumnPartitionedCSC(n, n, t(cp), t(ro), t(vo), rank, world, ops)
+    y = torch.zeros(P.nrow_local, dtype=torch.float64, device=device)
+    P.spmv(t(xh[P.c0:P.c0 + P.ncol_local]), y)
+    got = y.cpu().numpy()
+    sl = slice(P.r0, P.r0 + P.nrow_local)
+    den = np.maximum(scale[sl], 1e-300)
+    err = torch.tensor([float(np.max(np.abs(got - want[sl]) / den)) if len(got) else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    out["csc_column_blocks_reduce_scatter"] = {"ok": bool(err.item() <= 1e-12), "max_row_error": float(err.item()), "tolerance": 1e-12,
+                                               "matrix": f"uniform {n}x{n}, {nnz} entries", "gpus": world}
+    # ---- (2) the C++ *MatVectorNuma calls on G = world GPUs (one process drives all of them)
+    res = {"ok": None}
+    if rank == 0:
+        exe = os.path.join(ROOT, "bin", "api_check")
+        gold = os.path.join(ROOT, "tests", "golden", "api_rand90")
+        if os.path.exists(exe):
+            with tempfile.TemporaryDirectory() as tmp:
+                r = subprocess.run([exe, os.path.join(gold, "matrix.mtx"), tmp, str(world)], capture_output=True, text=True, timeout=300)
+                ld = lambda d, f: np.fromfile(os.path.join(d, f), dtype=np.float64)
+                ok = r.returncode == 0
+                detail = {}
+                if ok:
+                    one = ld(gold, "y_csr_copy.f64")          # y of the unmodified reference build (fixture)
+                    acc = np.zeros_like(one)
+                    for _ in range(50):                        # NTESTS accumulations (src/mat_vec.cpp:270)
+                        acc = acc + one
+                    detail["csr_bits"] = bool(ld(tmp, "y_csr_numa.f64").tobytes() == acc.tobytes())
+                    for f in ("ell", "coo", "csc"):
+                        detail[f + "_close"] = bool(np.max(np.abs(ld(tmp, f"y_{f}_numa.f64") - acc)) <= 1e-11 * max(1.0, float(np.max(np.abs(acc)))))
+                    ok = all(detail.values())
+                res = {"ok": bool(ok), "gpus": world, "fixture": "tests/golden/api_rand90 (y from the reference build)", **detail}
+                if r.returncode != 0:
+                    res["stderr"] = r.stderr[-300:]
+        else:
+            res = {"ok": None, "skipped": "bin/api_check not built"}
+    dist.barrier()
+    out["cpp_matvec_numa"] = res
+    return out
 
 
 def run_multi(args):
     from arm_spmv_b200 import power
-    power.bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler)
+    pre = None
+    if not args.no_preflight and env_int("WORLD_SIZE", 1) > 1:
+        import torch
+        import torch.distributed as dist
+        local = env_int("LOCAL_RANK", 0)
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+        try:
+            pre = preflight_multi(env_int("RANK", 0), env_int("WORLD_SIZE", 1), device)
+        except Exception as e:
+            pre = {"error": f"{type(e).__name__}: {e}"[:300]}
+    rc = power.bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler, extra={"preflight": pre} if pre else None)
+    bad = pre is not None and ("error" in pre or any(isinstance(v, dict) and v.get("ok") is False for v in pre.values()))
+    if bad or rc:
+        sys.exit(1)
 
 
 def main():
@@ -399,6 +550,8 @@ def main():
     ap.add_argument("--exchange", default="xchg,allgather,halo",
                     help="x refresh modes to time at N>1 (also: cepush, push, fused); the first that works is `value`")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap interior rows with the x refresh")
+    ap.add_argument("--no-preflight", action="store_true", help="N>1: skip the small partitioned-path checks before the timed runs")
+    ap.add_argument("--no-one-gpu", action="store_true", help="N>1: do not time the same workload on rank 0's GPU alone first")
     ap.add_argument("--iterated-grid", type=int, default=512, help="N=1: also time the power-iteration loop on this grid (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -120,6 +120,13 @@ THSP_API int thsp_csr_plan_spmv_f64(const thsp_csr_plan* plan, const double* x, 
                                     thsp_stream_t stream);
 THSP_API int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, int accumulate,
                                     thsp_stream_t stream);
+/* The product, and in the same pass the sum of squares of each TILE of 32 consecutive rows of the result:
+ * tile_ss[t] = y[32t]^2 + ... + y[32t+31]^2 added as an xor-butterfly (offsets 16, 8, 4, 2, 1), ceil(nrow/32) doubles.
+ * With thsp_tree_sum_f64 this is vec_dot(y, y) (src/vec_vec.cpp:15-29) in an order that does not depend on how the
+ * rows are spread over GPUs (csrc/tree_sum.cuh); the stream kernel writes the partials from its epilogue, so y is not
+ * read again - the other kernels are followed by thsp_tile_sumsq_f64. */
+THSP_API int thsp_csr_plan_spmv_sumsq_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate,
+                                          double* tile_ss, thsp_stream_t stream);
 /* Same, with HOST x and y (pinned or pageable): H2D of x, kernel, D2H of y, then synchronises.
  * This is the call bench.py times for its end-to-end number. */
 THSP_API int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host,
@@ -190,6 +197,14 @@ THSP_API int thsp_exclusive_scan_i32(int n, const int* counts, int* out, thsp_st
  * after a stream synchronise.  The _dev form leaves the scalar on the device (no sync). */
 THSP_API int thsp_dot_f64(int64_t n, const double* x, const double* y, double* result_host, thsp_stream_t stream);
 THSP_API int thsp_dot_dev_f64(int64_t n, const double* x, const double* y, double* result_dev, thsp_stream_t stream);
+/* vec_dot(y, y) in the canonical order of csrc/tree_sum.cuh, in two halves: per-tile partials (32 rows, butterfly), then
+ * the binary tree over the index bits of the m partials (absent ones count as +0.0) into *out_dev.  The tree half also
+ * combines the per-rank results of a partitioned vector (m = number of ranks). */
+THSP_API int thsp_tile_sumsq_f64(int64_t n, const double* y, double* tile_ss, thsp_stream_t stream);
+THSP_API int thsp_tree_sum_f64(int64_t m, const double* vals, double* out_dev, thsp_stream_t stream);
+/* Order-independent 64-bit fingerprint of v[0..n) sitting at global index first_index of a longer vector: pieces add up
+ * (mod 2^64) to the fingerprint of the whole.  bench.py compares row blocks on N GPUs with the one-GPU run. Synchronous. */
+THSP_API int thsp_hash_f64(int64_t n, const double* v, uint64_t first_index, uint64_t* hash_host, thsp_stream_t stream);
 /* vec_axpby (src/vec_vec.cpp:31-94): same seven branches, unfused multiply/add -> bit-exact. */
 THSP_API int thsp_axpby_f64(int64_t n, double alpha, const double* x, double beta, const double* y, double* w,
                             thsp_stream_t stream);
@@ -258,6 +273,15 @@ THSP_API int thsp_xchg_scale_push_f64(int64_t n, const double* y, uint64_t iter,
                                       void* work, double* x_local, int64_t offset, int ndest, double* const* dest_x,
                                       void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi,
                                       double* sumsq_out, thsp_stream_t stream);
+/* Both of the above in one kernel, fed by the per-tile sums of squares of thsp_csr_plan_spmv_sumsq_f64 (tile_ss, ceil(n/32)
+ * doubles for this rank's n rows): tree over the tiles, partial published to every rank, partials of all ranks combined
+ * by the same tree over rank numbers (csrc/tree_sum.cuh: same bits on 1, 2, 4, 8 GPUs for aligned row blocks), then the
+ * normalise + push + flags of thsp_xchg_scale_push_f64.  peer_ctrl[r] = control block of rank r (own one included).
+ * A peer that never publishes poisons *sumsq_out with NaN; x is then left untouched. */
+THSP_API int thsp_xchg_norm_scale_push_f64(int64_t n, const double* y, const double* tile_ss, uint64_t iter, int world, int rank,
+                                           void* const* peer_ctrl, void* work, double* x_local, int64_t offset, int ndest,
+                                           double* const* dest_x, void* const* dest_ctrl, const int64_t* dest_lo,
+                                           const int64_t* dest_hi, double* sumsq_out, thsp_stream_t stream);
 /* stream-ordered wait until the ranks in src_mask have raised their halo flag for `iter` */
 THSP_API int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stream_t stream);
 /* *flag_host = 1 if a wait of this rank gave up (~15 s) instead of hanging the GPU */

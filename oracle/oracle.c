@@ -97,6 +97,20 @@ ORACLE_API void oracle_ell_spmv(int nrow, int width, const int *ci, const double
     }
 }
 
+/* fp32 extension of the same sweep (no reference counterpart, SURVEY.md 8(c) "fp32"): same order in float. */
+ORACLE_API void oracle_ell_spmv_f32(int nrow, int width, const int *ci, const float *v,
+                                    const float *x, float *y)
+{
+    for (int s = 0; s < width; ++s) {
+        const int *cs = ci + (size_t)s * nrow;
+        const float *vs = v + (size_t)s * nrow;
+        for (int r = 0; r < nrow; ++r) {
+            float t = vs[r] * x[cs[r]];
+            y[r] = y[r] + t;
+        }
+    }
+}
+
 /* src/mat_vec.cpp:123-146  DIAMatrixMatVector: row-major diagonals, d ascending, accumulate
  * into y; the column guard compares against nrow (not ncol) exactly as the reference does. */
 ORACLE_API void oracle_dia_spmv(int nrow, int ndiags, const int *off, const double *v,
@@ -408,4 +422,52 @@ ORACLE_API void oracle_gen_rmat_coo(int scale, int64_t nnz, uint64_t seed, int *
         ri[k] = r; ci[k] = c;
         v[k] = u01(mix64(s));
     }
+}
+
+/* ------------------------------------------- canonical sum of squares + fingerprint -- */
+/* No reference counterpart: vec_dot (src/vec_vec.cpp:15-29) leaves its reduction order to OpenMP.  These restate the
+ * order the CUDA library fixes for the iterated loop (arm-spmv_b200/csrc/tree_sum.cuh) so that tests can demand the
+ * same bits: tiles of 32 rows reduced by an xor-butterfly, then the binary tree over index bits, absent elements
+ * counting as +0.0. */
+ORACLE_API void oracle_tile_sumsq(int64_t n, const double *y, double *tile_ss)
+{
+    int64_t ntiles = (n + 31) / 32;
+    for (int64_t t = 0; t < ntiles; ++t) {
+        double v[32], w[32];
+        for (int l = 0; l < 32; ++l) {
+            int64_t i = t * 32 + l;
+            double a = i < n ? y[i] : 0.0;
+            v[l] = a * a;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            for (int l = 0; l < 32; ++l) w[l] = v[l] + v[l ^ o];
+            for (int l = 0; l < 32; ++l) v[l] = w[l];
+        }
+        tile_ss[t] = v[0];
+    }
+}
+
+/* index-bit tree: at level L element i (a multiple of 2^(L+1)) takes in element i + 2^L */
+ORACLE_API double oracle_tree_sum(int64_t m, const double *vals)
+{
+    if (m <= 0) return 0.0;
+    double *a = (double *)malloc(sizeof(double) * (size_t)m);
+    memcpy(a, vals, sizeof(double) * (size_t)m);
+    for (int64_t s = 1; s < m; s <<= 1)
+        for (int64_t i = 0; i + s < m; i += 2 * s) a[i] = a[i] + a[i + s];
+    double r = a[0];
+    free(a);
+    return r;
+}
+
+/* order-independent fingerprint of v[0..n) placed at global index `first` (twin of thsp_hash_f64) */
+ORACLE_API uint64_t oracle_hash_f64(int64_t n, const double *v, uint64_t first)
+{
+    uint64_t h = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t b;
+        memcpy(&b, v + i, 8);
+        h += mix64(b ^ mix64(first + (uint64_t)i));
+    }
+    return h;
 }

@@ -216,6 +216,28 @@ class Oracle(_Base):
         self.fn("csr_spmv_f32")(C.c_int(nrow), _vp(rp), _vp(ci), _vp(v), _vp(x), _vp(y))
         return y
 
+    def ell_spmv_f32(self, nrow, width, ci, v, x, y):
+        y = np.ascontiguousarray(y, np.float32).copy()
+        ci = _i(ci)
+        v = np.ascontiguousarray(v, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        self.fn("ell_spmv_f32")(C.c_int(nrow), C.c_int(width), _vp(ci), _vp(v), _vp(x), _vp(y))
+        return y
+
+    def tile_sumsq(self, y):
+        y = _d(y)
+        out = np.zeros((len(y) + 31) // 32, np.float64)
+        self.fn("tile_sumsq")(C.c_int64(len(y)), _vp(y), _vp(out))
+        return out
+
+    def tree_sum(self, vals):
+        vals = _d(vals)
+        return float(self.fn("tree_sum", C.c_double)(C.c_int64(len(vals)), _vp(vals)))
+
+    def hash_f64(self, v, first=0):
+        v = _d(v)
+        return int(self.fn("hash_f64", C.c_uint64)(C.c_int64(len(v)), _vp(v), C.c_uint64(first)))
+
     def partition(self, n, nparts, part):
         s, c = C.c_int(), C.c_int()
         self.fn("partition")(C.c_int(n), C.c_int(nparts), C.c_int(part), C.byref(s), C.byref(c))

@@ -114,3 +114,100 @@ def test_host_vector_shared_by_the_ranks(thsp, cuda, oracle, n, rank, world):
         assert lo <= first <= max(0, A.start - n * n) and min(N - 1, A.start + A.count - 1 + n * n) <= last <= hi
     finally:
         xs.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 4096 * 32 - 5, 4096 * 32, 4096 * 32 + 1, 3_000_001])
+def test_canonical_sum_of_squares_matches_the_oracle_bits(thsp, cuda, oracle, n):
+    """thsp_tile_sumsq_f64 + thsp_tree_sum_f64 (csrc/tree_sum.cuh: 32-row butterfly, index-bit tree) against the
+    restatement in oracle.c, bit for bit, around the tile and 4096-tile block sizes; thsp_hash_f64 against its twin,
+    and additive over pieces."""
+    from arm_spmv_b200.lib import check, current_stream
+    lib = thsp.load()
+    y = oracle.gen_vector(n, 21) - 0.4
+    yd = torch.from_numpy(y).cuda()
+    tiles = torch.empty((n + 31) // 32, dtype=torch.float64, device="cuda")
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    check(lib.thsp_tile_sumsq_f64(C.c_int64(n), _p(yd), _p(tiles), current_stream()))
+    check(lib.thsp_tree_sum_f64(C.c_int64(tiles.numel()), _p(tiles), _p(out), current_stream()))
+    want_tiles = oracle.tile_sumsq(y)
+    assert tiles.cpu().numpy().tobytes() == want_tiles.tobytes()
+    assert float(out.item()) == oracle.tree_sum(want_tiles)
+    assert abs(float(out.item()) - float(np.dot(y, y))) <= 1e-13 * float(np.dot(y, y))
+    h = C.c_uint64(0)
+    check(lib.thsp_hash_f64(C.c_int64(n), _p(yd), C.c_uint64(77), C.byref(h), current_stream()))
+    assert h.value == oracle.hash_f64(y, 77)
+    cut = n // 3
+    h1, h2 = C.c_uint64(0), C.c_uint64(0)
+    check(lib.thsp_hash_f64(C.c_int64(cut), _p(yd), C.c_uint64(77), C.byref(h1), current_stream()))
+    check(lib.thsp_hash_f64(C.c_int64(n - cut), C.c_void_p(yd.data_ptr() + 8 * cut), C.c_uint64(77 + cut), C.byref(h2), current_stream()))
+    assert (h1.value + h2.value) % (1 << 64) == h.value
+
+
+@pytest.mark.parametrize("kernel", ["stream", "scalar", "merge"])
+def test_spmv_epilogue_leaves_the_tile_sums(thsp, cuda, oracle, kernel):
+    """thsp_csr_plan_spmv_sumsq_f64: y = A x and, from the same pass (stream kernel) or a pass over y (the others), the
+    sum of squares of every 32-row tile - the oracle's bits for the in-order kernels."""
+    from arm_spmv_b200 import host as H
+    from arm_spmv_b200.lib import check, current_stream
+    lib = thsp.load()
+    n = 21
+    N = n ** 3          # 9261 rows: the last tile is ragged
+    A = H.stencil27_csr(n)
+    check(lib.thsp_csr_plan_set_kernel(A.plan(), {"scalar": 1, "stream": 3, "merge": 4}[kernel], 1))
+    x = H.gen_vector(N, 3)
+    y = torch.empty(N, dtype=torch.float64, device="cuda")
+    tiles = torch.full(((N + 31) // 32,), float("nan"), dtype=torch.float64, device="cuda")
+    check(lib.thsp_csr_plan_spmv_sumsq_f64(A.plan(), _p(x.values), _p(y), 0, _p(tiles), current_stream()))
+    torch.cuda.synchronize()
+    rp, ci, va = oracle.gen_stencil27_csr(n)
+    want = oracle.csr_spmv(N, N, rp, ci, va, oracle.gen_vector(N, 3), np.zeros(N))
+    if kernel != "merge":
+        assert y.cpu().numpy().tobytes() == want.tobytes()
+    assert tiles.cpu().numpy().tobytes() == oracle.tile_sumsq(y.cpu().numpy()).tobytes()
+
+
+@pytest.mark.parametrize("n_total,halo", [(64 * 4096 * 2, 70_000), (100_032, 517), (64, 32)])
+def test_two_virtual_ranks_one_kernel(thsp, cuda, oracle, n_total, halo):
+    """thsp_xchg_norm_scale_push_f64 with two virtual ranks on one GPU: the sum is the oracle's canonical sum of the WHOLE
+    vector bit for bit (aligned halves are subtrees of one tree), both ranks hold the same bits, the pieces arrive."""
+    from arm_spmv_b200.lib import check
+    lib = thsp.load()
+    world = 2
+    per = n_total // world
+    parts = [(0, per), (per, n_total - per)]
+    ranks = [VirtualRank(lib, r, world, n_total, *parts[r]) for r in range(world)]
+    ctrl_arr = (C.c_void_p * world)(*[r.ctrl.data_ptr() for r in ranks])
+    h = min(halo, per)
+    dests = {0: (1, per - h, per), 1: (0, per, per + h)}
+    torch.cuda.synchronize()
+    for it in range(1, 4):
+        yall = oracle.gen_vector(n_total, 30 + it) - 0.3
+        ys = [torch.from_numpy(yall[s:s + c]).cuda() for s, c in parts]
+        tiles = [torch.from_numpy(oracle.tile_sumsq(yall[s:s + c])).cuda() for s, c in parts]
+        torch.cuda.synchronize()
+        for r in ranks:
+            with torch.cuda.stream(r.stream):
+                s = C.c_void_p(r.stream.cuda_stream)
+                other, lo, hi = dests[r.rank]
+                dx = (C.c_void_p * 1)(ranks[other].x.data_ptr())
+                dc = (C.c_void_p * 1)(ranks[other].ctrl.data_ptr())
+                dlo, dhi = (C.c_int64 * 1)(lo), (C.c_int64 * 1)(hi)
+                check(lib.thsp_xchg_norm_scale_push_f64(C.c_int64(r.count), _p(ys[r.rank]), _p(tiles[r.rank]), C.c_uint64(it), world, r.rank,
+                                                        ctrl_arr, _p(r.work), _p(r.x), C.c_int64(r.start), 1, dx, dc, dlo, dhi, _p(r.ss), s))
+                check(lib.thsp_xchg_wait(_p(r.ctrl), C.c_uint64(it), C.c_uint(1 << other), s))
+        torch.cuda.synchronize()
+        want = oracle.tree_sum(oracle.tile_sumsq(yall))
+        for r in ranks:
+            flag = C.c_int(1)
+            check(lib.thsp_xchg_timed_out(_p(r.ctrl), C.byref(flag), None))
+            assert flag.value == 0
+            if per % 32 == 0 and (per // 32) & (per // 32 - 1) == 0:
+                assert float(r.ss.item()) == want     # the halves are subtrees of the whole vector's tree
+            assert abs(float(r.ss.item()) - want) <= 1e-13 * want
+        assert ranks[0].ss.item() == ranks[1].ss.item()
+        inv = 1.0 / np.sqrt(ranks[0].ss.item())
+        for r in ranks:
+            own = r.x[r.start:r.start + r.count]
+            assert torch.equal(own, ys[r.rank] * inv)
+            other, lo, hi = dests[r.rank]
+            assert torch.equal(ranks[other].x[lo:hi], r.x[lo:hi])

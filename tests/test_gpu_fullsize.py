@@ -148,3 +148,91 @@ def test_spmv_full_size_formats_agree(thsp, cuda, which):
     ref32 = _csr_kernel(H, 1, 1, H.CSRMatrix(nrow=B.nrow, ncol=B.ncol, row_ptr=B.row_ptr, col_ind=B.col_ind,
                                              values=B.values.to(torch.float32).to(torch.float64)), x.to(torch.float32).to(torch.float64))
     assert _max_row_err(y32.to(torch.float64), ref32, scale) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The same full sizes against the REFERENCE ITSELF (oracle/_ref/libref.so = the unmodified sources compiled by
+# oracle/Makefile; it travels to the GPU box prebuilt), the C restatement when that library is absent.
+def _checker():
+    import pyoracle
+    pyoracle.build()
+    try:
+        r = pyoracle.Ref()
+        r.set_threads(max(1, min(16, len(__import__("os").sched_getaffinity(0)))))
+        return r, "reference"
+    except (FileNotFoundError, OSError):
+        return pyoracle.Oracle(), "port"
+
+
+def _np(t):
+    torch.cuda.synchronize()
+    return t.detach().cpu().numpy()
+
+
+def test_conversions_config3_equal_the_reference_constructors(thsp, cuda):
+    """configs[3], 128 M unsorted entries: CSRMatrix(COO), CSCMatrix(COO), ELLMatrix(COO) of the reference
+    (src/matrix.cpp:115-154, 295-325, 450-500; serial counting sorts, a few seconds each on the host) against the
+    GPU conversions - every index, value and diagonal array compared byte for byte."""
+    from arm_spmv_b200 import host as H
+    from gpu_util import assert_bits
+    chk, kind = _checker()
+    nrow = ncol = 1 << 23
+    A = H.uniform_coo(nrow, ncol, 1 << 27, 43)
+    ri, ci, va = _np(A.row_ind), _np(A.col_ind), _np(A.values)
+    B = H.CSRMatrix(A)
+    rp, co, vo, dg = chk.coo2csr(nrow, ncol, ri, ci, va)
+    assert_bits(_np(B.row_ptr), rp, f"row_ptr vs {kind}")
+    assert_bits(_np(B.col_ind), co, f"CSR col_ind vs {kind}")
+    assert_bits(_np(B.values), vo, f"CSR values vs {kind}")
+    assert B.ndiag == len(dg)
+    assert_bits(_np(B.diagonal[:B.ndiag]), dg, f"CSR diagonal vs {kind}")
+    del B, rp, co, vo
+    Cc = H.CSCMatrix(A)
+    cp, ro, vo = chk.coo2csc(nrow, ncol, ri, ci, va)
+    assert_bits(_np(Cc.col_ptr), cp, f"col_ptr vs {kind}")
+    assert_bits(_np(Cc.row_ind), ro, f"CSC row_ind vs {kind}")
+    assert_bits(_np(Cc.values), vo, f"CSC values vs {kind}")
+    del Cc, cp, ro, vo
+    D = H.ELLMatrix(A)
+    k, eco, eva, edg = chk.coo2ell(nrow, ncol, ri, ci, va)
+    assert D.nonzeros_in_row == k
+    assert_bits(_np(D.col_ind), eco, f"ELL col_ind vs {kind}")
+    assert_bits(_np(D.values), eva, f"ELL values vs {kind}")
+    assert_bits(_np(D.diagonal[:D.ndiag]), edg, f"ELL diagonal vs {kind}")
+
+
+def test_stencil_256_spmv_equals_the_reference_bit_for_bit(thsp, cuda, oracle):
+    """configs[1]: y += A x of the reference's own CSRMatrixMatVector / ELLMatrixMatVector / DIAMatrixMatVector
+    (src/mat_vec.cpp:44-67, 97-121, 123-146) on the 256^3 stencil against the GPU kernels, same bits.  The matrix
+    arrays the GPU generator makes are first checked against the oracle's generator."""
+    from arm_spmv_b200 import host as H
+    from gpu_util import assert_bits
+    chk, kind = _checker()
+    n = 256
+    N = n ** 3
+    rp, ci, va = oracle.gen_stencil27_csr(n)
+    xh = oracle.gen_vector(N, 11)
+    A = H.stencil27_csr(n)
+    x = H.gen_vector(N, 11)
+    assert_bits(_np(A.row_ptr), rp, "stencil row_ptr")
+    assert_bits(_np(A.col_ind), ci, "stencil col_ind")
+    assert_bits(_np(A.values), va, "stencil values")
+    assert_bits(_np(x.values), xh, "x")
+    y0 = oracle.gen_vector(N, 12)
+    want = chk.csr_spmv(N, N, rp, ci, va, xh, y0)
+    for kernel in (3, 1):   # stream (the plan's choice) and scalar: the reference's order
+        y = H.Vector(y0)
+        H.csr_spmv_kernel(kernel, 1, A, x.values, y.values, True)
+        assert_bits(_np(y.values), want, f"CSR kernel {kernel} vs {kind}")
+    del rp, ci, va
+    D = H.DIAMatrix(A)
+    yd = H.Vector(y0)
+    H.DIAMatrixMatVector(D, x, yd)
+    wantd = chk.dia_spmv(N, N, _np(D.offsets), _np(D.values), xh, y0)
+    assert_bits(_np(yd.values), wantd, f"DIA vs {kind}")
+    del D, A, wantd
+    E = H.stencil27_ell(n)
+    ye = H.Vector(y0)
+    H.ELLMatrixMatVector(E, x, ye)
+    wante = chk.ell_spmv(N, N, 27, _np(E.col_ind), _np(E.values), xh, y0)
+    assert_bits(_np(ye.values), wante, f"ELL vs {kind}")

@@ -313,3 +313,28 @@ def test_csr_host_buffer_path(thsp, cuda, oracle, which, accumulate):
             assert max_row_error(yh.numpy(), ref, row_scale_csr(nrow, rp, ci, va, x), y0 if accumulate else None) <= TOL64
     # the launch counter counts graph replays kernel by kernel and does not count the capture itself
     assert 9 <= thsp.lib.launch_count() - launches0 < 1000
+
+
+@pytest.mark.parametrize("nrow_pad", [0, 1, 2, 3])
+def test_ell_fp32(thsp, cuda, oracle, nrow_pad):
+    """thsp_ell_spmv_f32 (the fp32 extension of ELLMatrixMatVector, src/mat_vec.cpp:97-121): the slot-by-slot order in
+    float is kept, so the result equals the float restatement bit for bit - with nrow a multiple of 4 (128-bit loads,
+    four rows per thread) and not (one row per thread) - and stays within 1e-5 of the fp64 sum of the rounded inputs."""
+    import ctypes as C
+    from arm_spmv_b200.lib import check, current_stream, load, ptr
+    nrow0, ncol, rp, ci, va = synthetic(oracle, "stencil12")
+    ri = np.repeat(np.arange(nrow0, dtype=np.int32), np.diff(rp))
+    nrow = nrow0 - nrow_pad          # drop the last rows: 1728 is a multiple of 4, 1727/1726/1725 are not
+    keep = ri < nrow
+    ri, ci, va = ri[keep], ci[keep], va[keep]
+    k, eco, eva, _ = oracle.coo2ell(nrow, ncol, ri, ci, va)
+    x = (oracle.gen_vector(ncol, 7) - 0.5).astype(np.float32)
+    y0 = oracle.gen_vector(nrow, 8).astype(np.float32)
+    v32 = eva.astype(np.float32)
+    want = oracle.ell_spmv_f32(nrow, k, eco, v32, x, y0)
+    y = dev(y0)
+    check(load().thsp_ell_spmv_f32(nrow, ncol, k, ptr(dev(eco)), ptr(dev(v32)), ptr(dev(x)), ptr(y), current_stream()))
+    assert_bits(host(y), want, "ELL fp32")
+    ref64 = oracle.ell_spmv(nrow, ncol, k, eco, v32.astype(np.float64), x.astype(np.float64), y0.astype(np.float64))
+    scale = row_scale_coo(nrow, ri, ci, va.astype(np.float32).astype(np.float64), x.astype(np.float64))
+    assert max_row_error(host(y).astype(np.float64), ref64, scale, y0.astype(np.float64)) <= TOL32

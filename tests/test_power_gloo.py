@@ -40,9 +40,17 @@ class OracleOps:
     def csr_block(self, nrow, ncol, row_ptr, col_ind, values):
         return (nrow, ncol, row_ptr.numpy(), col_ind.numpy(), values.numpy()), int(col_ind.numel())
 
-    def spmv(self, payload, x, y):
+    def spmv(self, payload, x, y, tile_ss=None):
         nrow, ncol, rp, ci, va = payload
         y.copy_(torch.from_numpy(self.O.csr_spmv(nrow, ncol, rp, ci, va, x.numpy(), np.zeros(nrow))))
+        if tile_ss is not None:   # the SpMV's epilogue: sum of squares per tile of 32 rows (csrc/tree_sum.cuh)
+            tile_ss.copy_(torch.from_numpy(self.O.tile_sumsq(y.numpy())))
+
+    def tree_sum(self, vals, out):
+        out[0] = self.O.tree_sum(vals.numpy())
+
+    def hash(self, v, first):
+        return self.O.hash_f64(v.numpy(), first)
 
     def sumsq(self, y, out):
         out[0] = self.O.dot(y.numpy(), y.numpy())
@@ -77,15 +85,10 @@ class OracleOps:
     def wait_halo(self, it, src_mask):
         pass   # the emulated push below is synchronous
 
-    def sumsq_publish(self, y, it):
-        self.partial = self.O.dot(y.numpy(), y.numpy())
-
-    def scale_push(self, y, it, x, offset, ss):
+    def norm_scale_push(self, y, tile_ss, it, x, offset, ss):
         parts = [None] * self.xw
-        dist.all_gather_object(parts, self.partial)
-        tot = 0.0
-        for p in parts:          # rank order, like xchg_scale_push_kernel
-            tot += p
+        dist.all_gather_object(parts, self.O.tree_sum(tile_ss.numpy()))
+        tot = self.O.tree_sum(np.array(parts))   # tree over rank numbers, like xchg_norm_scale_push_kernel
         ss[0] = tot
         w = torch.from_numpy(self.O.axpby(1.0 / np.sqrt(tot), y.numpy(), 0.0, y.numpy()))
         x[offset:offset + y.numel()] = w
@@ -100,16 +103,18 @@ class OracleOps:
                     x[lo:hi] = data
 
 
-def serial_power_iteration(O, n, steps, seed):
+def serial_power_iteration(O, n, steps, seed, canonical=False):
+    """The loop composed from the reference's calls; canonical: vec_dot(y, y) in the fixed order of
+    csrc/tree_sum.cuh instead of the serial sum - what one GPU computes."""
     N = n ** 3
     rp, ci, va = O.gen_stencil27_csr(n)
     x = O.gen_vector(N, seed)
     nrm = 0.0
     for _ in range(steps):
         y = O.csr_spmv(N, N, rp, ci, va, x, np.zeros(N))
-        nrm = np.sqrt(O.dot(y, y))
+        nrm = np.sqrt(O.tree_sum(O.tile_sumsq(y)) if canonical else O.dot(y, y))
         x = O.axpby(1.0 / nrm, y, 0.0, y)
-    return x, nrm
+    return x, nrm, y
 
 
 def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
@@ -128,7 +133,7 @@ def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
         for _ in range(steps):
             it.step()
         # after the last refresh every replica must hold the same, complete x (xchg: only the pieces it reads)
-        torch.save({"x": it.x.clone(), "norm": it.norm(), "start": A.start, "count": A.count, "needs": A.needed_ranges(),
+        torch.save({"x": it.x.clone(), "norm": it.norm(), "y": it.y.clone(), "y_hash": it.y_hash(), "start": A.start, "count": A.count, "needs": A.needed_ranges(),
                     "blocks": [(b.row0, b.nrow, b.boundary) for b in A.blocks]}, f"{out}.{rank}")
     finally:
         dist.destroy_process_group()
@@ -137,17 +142,34 @@ def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
 @pytest.mark.parametrize("world,n,overlap,generic,mode", [(2, 6, True, False, "allgather"), (2, 7, False, False, "allgather"),
                                                           (3, 5, True, False, "allgather"), (2, 6, True, True, "allgather"),
                                                           (2, 6, True, False, "xchg"), (3, 5, True, False, "xchg"),
-                                                          (3, 6, False, True, "xchg")])
+                                                          (3, 6, False, True, "xchg"),
+                                                          (2, 8, True, False, "xchg"), (4, 8, True, False, "allgather"),
+                                                          (2, 8, False, True, "allgather")])
 def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, overlap, generic, mode):
     steps = 4
     port = 29500 + (os.getpid() + world * 7 + n + len(mode)) % 400
     out = str(tmp_path / "res")
     mp.spawn(_worker, args=(world, port, n, steps, mode, overlap, generic, out), nprocs=world, join=True)
-    x_ref, nrm_ref = serial_power_iteration(oracle, n, steps, 5)
+    x_ref, nrm_ref, _ = serial_power_iteration(oracle, n, steps, 5)
+    # Row blocks that are whole subtrees of the canonical sum (n^3 a multiple of 32 * world, world a power of two):
+    # norm, x and y must equal the ONE-rank loop bit for bit, and the ranks' fingerprints of y add up to its fingerprint.
+    aligned = (n ** 3) % (32 * world) == 0 and world & (world - 1) == 0
+    if aligned:
+        x_one, nrm_one, y_one = serial_power_iteration(oracle, n, steps, 5, canonical=True)
+        hsum = 0
     covered = 0
     for r in range(world):
         res = torch.load(f"{out}.{r}")
         assert res["start"] == covered
+        if aligned:
+            lo, hi = res["start"], res["start"] + res["count"]
+            assert res["norm"] == nrm_one, (res["norm"], nrm_one)
+            assert res["x"].numpy()[lo:hi].tobytes() == x_one[lo:hi].tobytes()
+            assert res["y"].numpy().tobytes() == y_one[lo:hi].tobytes()
+            assert res["y_hash"] == oracle.hash_f64(y_one[lo:hi], lo)
+            hsum = (hsum + res["y_hash"]) % (1 << 64)
+            if r == world - 1:
+                assert hsum == oracle.hash_f64(y_one, 0)
         covered += res["count"]
         # rows are multiplied in the reference's order, so only the norm (a sum over ranks) differs in rounding
         if mode == "xchg":   # a replica is refreshed only where this rank reads it: own slice + needed pieces
@@ -175,6 +197,7 @@ def test_stencil_row_blocks_cover_and_flag_boundaries(oracle):
             at = start
             for r0, r1, bnd in sorted(pieces):
                 assert r0 == at and r1 > r0
+                assert (r0 - start) % 32 == 0, "pieces start on tile boundaries of the slice (canonical sum of squares)"
                 at = r1
                 cols = ci[rp[r0]:rp[r1]]
                 needs_remote = cols.min() < start or cols.max() >= start + count
