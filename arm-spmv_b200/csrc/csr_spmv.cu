@@ -102,6 +102,7 @@ struct StreamCfg {
     int warps;   // per CTA
     int stages;  // ring depth per warp
     int chunk;   // CH
+    int tile_stride = 1;   // TS: tiles per grid line of a matrix from a regular grid (1 = plain round-robin)
 };
 
 template <typename V>
@@ -117,7 +118,7 @@ template <typename V>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
-                      V* __restrict__ tile_ss)
+                      V* __restrict__ tile_ss, int TS, int* __restrict__ stale)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -138,14 +139,38 @@ __global__ void __launch_bounds__(768, 1)
     }
     __syncwarp();
 
+    // A plan remembers the entry count; a caller that rewrote row_ptr in place since (the classes expose raw pointers,
+    // include/matrix.h) must not be served with bulk copies bounded by the old count: every warp sees the same
+    // row_ptr[nrow], so all of them leave together, nothing is written, and the host finds the flag (thsp_csr_plan_stale).
+    if (stale && __ldg(row_ptr + nrow) != nnz) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) *stale = 1;
+        return;
+    }
     const int num_tiles = (nrow + 31) >> 5;
-    const int GW = gridDim.x * W;
-    const int gw = blockIdx.x * W + warp;
     const int nnz_al = nnz & ~3;
     const uint64_t pol = policy_evict_first();
+    // Which tile a warp takes at its q-th step.  The tiles are seen as lines of TS tiles; step B = q * grid + CTA of the
+    // whole grid is the x-position B % TS of line group B / TS, and the W warps of the CTA take that position in W
+    // CONSECUTIVE lines.  On a matrix from a regular grid whose rows lie TS tiles (one grid line) apart, the warps of a
+    // CTA then gather from x-lines they share (a row reads the lines above and below its own) and L1 serves what L2
+    // served before: profiles/r02_slab_*.  TS = 1 is the plain round-robin (tile = B * W + warp) for everything else.
+    // Steps that fall off the end of the matrix are skipped; num_tiles = done.
+    auto tile_of = [&](int& q) -> int {
+        while (true) {
+            const long long B = (long long)q * gridDim.x + blockIdx.x;
+            const long long lg = B / TS, xt = B - lg * TS;
+            if (lg * W * TS >= num_tiles) return num_tiles;
+            const long long t = (lg * W + warp) * TS + xt;
+            if (t < num_tiles) return (int)t;
+            ++q;
+        }
+    };
 
     // ---- producer cursor (warp-uniform): runs S chunks ahead of the consumer --------------
-    int p_tile = gw, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
+    int p_q = 0, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
+    int p_tile = tile_of(p_q);
+    int n_q = p_q + 1;
+    int n_tile = p_tile < num_tiles ? tile_of(n_q) : num_tiles;   // the tile after p_tile
     bool p_open = false;
     int pf_rs = 0, pf_re = 0;  // row bounds of p_tile, fetched one step ahead
     if (p_tile < num_tiles) {
@@ -154,7 +179,8 @@ __global__ void __launch_bounds__(768, 1)
         pf_re = __ldg(row_ptr + min(r + 1, nrow));
     }
     // ---- consumer cursor ------------------------------------------------------------------
-    int c_tile = gw, c_slot = 0, c_chunk = 0, c_nch = 1, c_al = 0, c_te = 0, c_stage = 0;
+    int c_q = 0, c_slot = 0, c_chunk = 0, c_nch = 1, c_al = 0, c_te = 0, c_stage = 0;
+    int c_tile = tile_of(c_q);
     unsigned c_parity = 0;
     int rs = 0, re = 0;
     V sum = V(0), yold = V(0);
@@ -173,9 +199,8 @@ __global__ void __launch_bounds__(768, 1)
                 p_nch = max(1, (p_te - p_al + CH - 1) / CH);
                 p_chunk = 0;
                 p_open = true;
-                const int nt = p_tile + GW;  // bounds of the tile after this one
-                if (nt < num_tiles) {
-                    const int r = nt * 32 + lane;
+                if (n_tile < num_tiles) {   // bounds of the tile after this one
+                    const int r = n_tile * 32 + lane;
                     pf_rs = __ldg(row_ptr + min(r, nrow));
                     pf_re = __ldg(row_ptr + min(r + 1, nrow));
                 }
@@ -203,7 +228,11 @@ __global__ void __launch_bounds__(768, 1)
             }
             p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
             if (++p_chunk == p_nch) {
-                p_tile += GW;
+                p_tile = n_tile;
+                if (n_tile < num_tiles) {
+                    ++n_q;
+                    n_tile = tile_of(n_q);
+                }
                 p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
                 p_open = false;
             }
@@ -261,7 +290,8 @@ __global__ void __launch_bounds__(768, 1)
                 for (int o = 16; o > 0; o >>= 1) q = add_rn(q, __shfl_xor_sync(full, q, o));
                 if (lane == 0) tile_ss[c_tile] = q;
             }
-            c_tile += GW;
+            ++c_q;
+            c_tile = tile_of(c_q);
             c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
             c_chunk = 0;
         }
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(768, 1)
 
 template <typename V>
 static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
-                      const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr)
+                      const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, int* stale = nullptr)
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
@@ -289,7 +319,8 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss);
+    const int ts = cfg.tile_stride >= 1 && (int64_t)cfg.tile_stride * cfg.warps <= num_tiles ? cfg.tile_stride : 1;
+    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, ts, stale);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -321,7 +352,8 @@ static StreamCfg default_stream_cfg(int nrow, int nnz)
 // of that merge, whatever the row lengths are - a run holds at most kMbRun entries and at most
 // kMbRun row ends, so neither a hub row nor a stretch of empty rows unbalances it.
 //   0. merge_partition_kernel: the (row, entry) coordinate where each run starts (binary search
-//      along the run's diagonal).  Part of the plan; the stateless entry point recomputes it.
+//      along the run's diagonal).  Recomputed by every call (~1 % of the product): a table kept in the plan would be
+//      derived from the contents of row_ptr and go stale silently when a caller rewrites them.
 //   1. every row that STARTS inside the run scatters its id to mark[start - first entry]
 //      (atomicMax, so of several empty rows starting at one entry the last - the non-empty one -
 //      wins): 2 KB of shared memory per warp, the only shared memory the kernel uses;
@@ -373,9 +405,13 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     csr_merge_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                              const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y,
                              const int* __restrict__ part_row, const int* __restrict__ part_ent, int* __restrict__ carry_row,
-                             V* __restrict__ carry_val, int nruns)
+                             V* __restrict__ carry_val, int nruns, int* __restrict__ stale)
 {
     __shared__ int s_mark_all[kMergeWarps][kMbPad];
+    if (stale && __ldg(row_ptr + nrow) != nnz) {   // see csr_stream_kernel: the run table was sized for another entry count
+        if (threadIdx.x == 0 && blockIdx.x == 0) *stale = 1;
+        return;
+    }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int run = blockIdx.x * kMergeWarps + (threadIdx.x >> 5);
@@ -501,8 +537,9 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
 
 template <typename V>
 __global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry_row, const V* __restrict__ carry_val,
-                                       V* __restrict__ y)
+                                       V* __restrict__ y, const int* __restrict__ row_ptr, int nrow, int nnz, const int* __restrict__ stale)
 {
+    if (stale && __ldg(row_ptr + nrow) != nnz) return;   // the main kernel did not run: the carries are not there
     // Slots are in entry order, so partials of one row are consecutive (ignoring -1 holes).
     // One thread per slot; the thread owning the FIRST slot of a row adds the whole chain in order.
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -555,7 +592,7 @@ static int merge_partition(int nrow, int nnz, const int* rp, int* part, cudaStre
 
 template <typename V>
 static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* val, const V* x, V* y, int acc,
-                     const int* part, cudaStream_t s)
+                     const int* part, cudaStream_t s, int* stale = nullptr)
 {
     if (!acc && nrow > 0) {
         zero_kernel<V><<<div_up(nrow, 256), 256, 0, s>>>(nrow, y);
@@ -575,10 +612,10 @@ static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* 
     const int* pr = part;
     const int* pe = part + nruns + 1;
     const bool vec = ((((uintptr_t)val) | ((uintptr_t)col)) & 31) == 0;   // 256-bit loads of whole sectors
-    if (vec) csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
-    else csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns);
+    if (vec) csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns, stale);
+    else csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns, stale);
     THSP_LAUNCH_CHECK();
-    csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y);
+    csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y, rp, nrow, nnz, stale);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -658,7 +695,10 @@ struct HostPipe {
 
 struct thsp_csr_plan {
     HostPipe* pipe = nullptr;
-    int* merge_part = nullptr;   // merge-path run coordinates (device), built when the merge kernel is first used
+    // Nothing here is derived from the contents of the arrays except nnz, the histogram and the kernel choice made from
+    // it: the merge-path run table is recomputed by every call (one binary search per run, ~1 % of the kernel), and the
+    // kernels that depend on nnz check it against row_ptr[nrow] and raise `stale` (pinned host memory the GPU can write).
+    int* stale = nullptr;
     int nrow, ncol, nnz, value_bytes;
     const int* row_ptr;
     const int* col_ind;
@@ -714,20 +754,51 @@ template <typename V>
 static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr)
 {
     if (p->nrow <= 0) return 0;
-    if (p->kernel == THSP_CSR_MERGE) {
-        if (!p->merge_part && p->nnz > 0) {   // the run table belongs to the matrix: build it once
-            thsp_csr_plan* mp = const_cast<thsp_csr_plan*>(p);
-            const int nruns = merge_runs(p->nrow, p->nnz);
-            THSP_CUDA(cudaMalloc(&mp->merge_part, sizeof(int) * 2 * ((size_t)nruns + 1)));
-            if (merge_partition(p->nrow, p->nnz, p->row_ptr, mp->merge_part, s)) return 1;
-        }
-        return run_merge<V>(p->nrow, p->nnz, p->row_ptr, p->col_ind, static_cast<const V*>(p->val), x, y, acc, p->merge_part, s);
-    }
+    if (p->kernel == THSP_CSR_MERGE)
+        return run_merge<V>(p->nrow, p->nnz, p->row_ptr, p->col_ind, static_cast<const V*>(p->val), x, y, acc, nullptr, s, p->stale);
     if (p->kernel == THSP_CSR_STREAM)
         return run_stream<V>(p->stream_cfg, p->ctas, p->nrow, p->nnz, p->row_ptr, p->col_ind,
-                             static_cast<const V*>(p->val), x, y, acc, s, tile_ss);
+                             static_cast<const V*>(p->val), x, y, acc, s, tile_ss, p->stale);
     return dispatch<V>(p->kernel, p->lanes, &p->stream_cfg, p->nrow, p->ncol, p->nnz, p->row_ptr, p->col_ind,
                        static_cast<const V*>(p->val), x, y, acc, s);
+}
+
+// Rows of a matrix from a regular grid read the grid lines above and below their own: the smallest column offset
+// beyond the row's own neighbours is the length of a grid line.  Three sample rows must agree on it; the stream kernel
+// then lets the warps of a CTA work one grid line apart (tile_of in csr_stream_kernel).  1 = no such structure.
+static int detect_tile_stride(int nrow, const int* row_ptr, const int* col_ind, cudaStream_t s)
+{
+    if (const char* e = getenv("THSP_TILE_STRIDE")) {
+        const int v = atoi(e);
+        if (v >= 1) return v;
+    }
+    if (nrow < 4096) return 1;
+    int agreed = 0;
+    for (int k = 1; k <= 3; ++k) {
+        const int r = (int)((int64_t)nrow * k / 4);
+        int b[2] = {0, 0};
+        if (cudaMemcpyAsync(b, row_ptr + r, sizeof(b), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        const int len = b[1] - b[0];
+        if (len < 3 || len > 128) return 1;
+        int cols[128];
+        if (cudaMemcpyAsync(cols, col_ind + b[0], sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        int d = 0;
+        for (int i = 0; i < len; ++i) {
+            const int off = cols[i] - r;
+            if (off > 1 && (d == 0 || off < d)) d = off;
+        }
+        if (d == 0 || (agreed && d != agreed)) return 1;
+        agreed = d;
+    }
+    const int ts = (agreed + 16) / 32;
+    return ts >= 2 && ts <= 4096 ? ts : 1;
 }
 
 extern "C" {
@@ -770,6 +841,12 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
     p->ctas = sm_count();
     for (int i = 0; i < 32; ++i) p->hist[i] = 0;
     p->max_len = 0;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p->stale), sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        p->stale = nullptr;   // no flag, no check: the plan still works
+    } else {
+        *p->stale = 0;
+    }
     if (nrow > 0) {
         unsigned long long* dh = static_cast<unsigned long long*>(scratch(33 * sizeof(unsigned long long), 4));
         if (!dh) { delete p; return 1; }
@@ -805,6 +882,7 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
         p->lanes = lanes_for_mean(mean);
     }
     p->stream_cfg = value_bytes == 8 ? default_stream_cfg<double>(nrow, nnz) : default_stream_cfg<float>(nrow, nnz);
+    if (p->kernel == THSP_CSR_STREAM) p->stream_cfg.tile_stride = detect_tile_stride(nrow, row_ptr, col_ind, s);
     *out = p;
     return 0;
 }
@@ -829,8 +907,15 @@ static void drop_host_pipe(thsp_csr_plan* plan)
 int thsp_csr_plan_destroy(thsp_csr_plan* plan)
 {
     if (plan) drop_host_pipe(plan);
-    if (plan && plan->merge_part) cudaFree(plan->merge_part);
+    if (plan && plan->stale) cudaFreeHost(plan->stale);
     delete plan;
+    return 0;
+}
+int thsp_csr_plan_stale(const thsp_csr_plan* plan, int* stale)
+{
+    THSP_REQUIRE(plan != nullptr && stale != nullptr, "null plan");
+    *stale = plan->stale ? *static_cast<volatile int*>(plan->stale) : 0;
+    if (plan->stale) *plan->stale = 0;
     return 0;
 }
 int thsp_csr_plan_kernel(const thsp_csr_plan* plan, int* kernel, int* lanes)

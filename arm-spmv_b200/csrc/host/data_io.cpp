@@ -54,6 +54,7 @@ void VectorWrite(const char* filename, const Vector& x)
 
 void COOMatrixRead(const char* filename, COOMatrix& A)
 {
+    Trace tr("COOMatrixRead");
     // Progress lines and failure behaviour follow src/data_io.cpp:52-91 (print, exit(1)).
     printf("\tOpening matrix market file\n");
     FILE* fp = fopen(filename, "r");
@@ -110,6 +111,10 @@ void COOMatrixRead(const char* filename, COOMatrix& A)
         va[k] = v;
     }
     if (fp != stdin) fclose(fp);
+    {   // the converting constructors come next and run once each (main.cpp:38-41): scratch and kernels ready before them
+        Trace tp("  prepare conversions");
+        ok(thsp_prepare_conversions(rows, cols, nz, nullptr), "conversion scratch");
+    }
     printf("### ROW=%d, COL=%d, NNZ=%d\n", rows, cols, nz);
     A.Free();
     A.nrow = rows;

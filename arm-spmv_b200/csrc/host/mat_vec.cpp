@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "hostmem.h"
@@ -21,10 +23,21 @@
 using namespace thsp_host;
 
 // ------------------------------------------------------------------------------------------
+// Matrix arrays: library-owned (managed) memory is used in place; arrays adopted from the caller
+// (src/matrix.cpp:12-15,88-91) get a device mirror that is uploaded once and found again on later calls
+// (hostmem.h mirror()).  x and y change between calls: host vectors are staged through pooled device buffers.
 void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y)
 {
-    View<int> ri(A.row_ind, A.nnz, false), ci(A.col_ind, A.nnz, false);
-    View<double> va(A.values, A.nnz, false), xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
+    if (A.nnz <= 0) return;
+    const int* ri = mirror(A.row_ind, A.nnz);
+    const int* ci = mirror(A.col_ind, A.nnz);
+    const double* va = mirror(A.values, A.nnz);
+    if (kind(A.values) == 2 && first_gpu_use(A.values)) {
+        prefetch_traced(A.row_ind, sizeof(int) * (size_t)A.nnz);
+        prefetch_traced(A.col_ind, sizeof(int) * (size_t)A.nnz);
+        prefetch_traced(A.values, sizeof(double) * (size_t)A.nnz);
+    }
+    View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
     ok(thsp_coo_spmv_f64(A.nrow, A.ncol, A.nnz, ri, ci, va, xv, yv, nullptr), "COO SpMV");
     sync();
     yv.commit();
@@ -33,41 +46,54 @@ void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y)
 void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y)
 {
     if (A.nrow <= 0) return;
-    const int k = kind(A.values);
     View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
-    if (k == 1 || k == 2) {
-        // Library-owned (managed) arrays: the plan remembers the kernel chosen from the row-length
-        // histogram and the entry count; creating it also brings the matrix into HBM.  Plans are
-        // dropped when the matrix is freed or reassigned (CSRMatrix::Free).
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // The plan remembers the kernel chosen from the row-length histogram and the entry count; creating it also
+        // brings a managed matrix into HBM / uploads the mirror of an adopted one.  Plans are dropped when the matrix
+        // is freed or reassigned (CSRMatrix::Free) and when a kernel finds that the entry count has changed.
         int nnz = 0;
-        thsp_csr_plan* plan = csr_plan(A.nrow, A.ncol, -1, A.row_ptr, A.col_ind, A.values, &nnz);
+        const int* rp = mirror(A.row_ptr, (size_t)A.nrow + 1);
+        thsp_csr_plan* plan = nullptr;
+        const int* ci = nullptr;
+        const double* va = nullptr;
+        const bool own = rp == A.row_ptr;   // device-usable in place
+        if (own) plan = csr_plan(A.nrow, A.ncol, -1, A.row_ptr, A.col_ind, A.values, &nnz);
         if (!plan) {
-            nnz = peek_int(A.row_ptr + A.nrow);
-            if (k == 2) {
+            nnz = own ? peek_int(A.row_ptr + A.nrow) : A.row_ptr[A.nrow];
+            ci = mirror(A.col_ind, (size_t)nnz);
+            va = mirror(A.values, (size_t)nnz);
+            if (own && kind(A.values) == 2) {
                 if (first_gpu_use(A.row_ptr)) prefetch_traced(A.row_ptr, sizeof(int) * ((size_t)A.nrow + 1));
                 if (nnz && first_gpu_use(A.col_ind)) prefetch_traced(A.col_ind, sizeof(int) * (size_t)nnz);
                 if (nnz && first_gpu_use(A.values)) prefetch_traced(A.values, sizeof(double) * (size_t)nnz);
             }
-            plan = csr_plan(A.nrow, A.ncol, nnz, A.row_ptr, A.col_ind, A.values);
+            plan = csr_plan(A.nrow, A.ncol, nnz, rp, ci, va);   // keyed by the DEVICE addresses: found again through the mirrors
         }
         ok(thsp_csr_plan_spmv_f64(plan, xv, yv, 1, nullptr), "CSR SpMV");
-    } else {
-        const int nnz = peek_int(A.row_ptr + A.nrow);
-        View<int> rp(A.row_ptr, (size_t)A.nrow + 1, false), ci(A.col_ind, nnz, false);
-        View<double> va(A.values, nnz, false);
-        ok(thsp_csr_spmv_f64(A.nrow, A.ncol, nnz, rp, ci, va, xv, yv, 1, nullptr), "CSR SpMV");
         sync();
+        int stale = 0;
+        ok(thsp_csr_plan_stale(plan, &stale), "CSR plan check");
+        if (!stale) break;
+        if (attempt == 1) die("CSR SpMV (row_ptr changes while the product runs)");
+        forget_plans(rp);   // row_ptr[nrow] is not what the plan was made for: nothing was written, plan again
+        if (!own) invalidate(A.row_ptr), invalidate(A.col_ind), invalidate(A.values);
     }
-    sync();
     yv.commit();
 }
 
 void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y)
 {
     if (A.ncol <= 0) return;
-    const int nnz = peek_int(A.col_ptr + A.ncol);
-    View<int> cp(A.col_ptr, (size_t)A.ncol + 1, false), ri(A.row_ind, nnz, false);
-    View<double> va(A.values, nnz, false), xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
+    const int* cp = mirror(A.col_ptr, (size_t)A.ncol + 1);
+    const int nnz = cp == A.col_ptr ? peek_int(A.col_ptr + A.ncol) : A.col_ptr[A.ncol];
+    const int* ri = mirror(A.row_ind, (size_t)nnz);
+    const double* va = mirror(A.values, (size_t)nnz);
+    if (kind(A.values) == 2 && first_gpu_use(A.values)) {
+        prefetch_traced(A.col_ptr, sizeof(int) * ((size_t)A.ncol + 1));
+        prefetch_traced(A.row_ind, sizeof(int) * (size_t)nnz);
+        prefetch_traced(A.values, sizeof(double) * (size_t)nnz);
+    }
+    View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
     ok(thsp_csc_spmv_f64(A.nrow, A.ncol, nnz, cp, ri, va, xv, yv, nullptr), "CSC SpMV");
     sync();
     yv.commit();
@@ -76,8 +102,14 @@ void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y)
 void ELLMatrixMatVector(const ELLMatrix& A, const Vector& x, Vector& y)
 {
     const size_t total = (size_t)A.nrow * (size_t)A.nonzeros_in_row;
-    View<int> ci(A.col_ind, total, false);
-    View<double> va(A.values, total, false), xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
+    if (total == 0) return;
+    const int* ci = mirror(A.col_ind, total);
+    const double* va = mirror(A.values, total);
+    if (kind(A.values) == 2 && first_gpu_use(A.values)) {
+        prefetch_traced(A.col_ind, sizeof(int) * total);
+        prefetch_traced(A.values, sizeof(double) * total);
+    }
+    View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
     ok(thsp_ell_spmv_f64(A.nrow, A.ncol, A.nonzeros_in_row, ci, va, xv, yv, nullptr), "ELL SpMV");
     sync();
     yv.commit();
@@ -86,9 +118,12 @@ void ELLMatrixMatVector(const ELLMatrix& A, const Vector& x, Vector& y)
 void DIAMatrixMatVector(const DIAMatrix& A, const Vector& x, Vector& y)
 {
     const size_t total = (size_t)A.nrow * (size_t)A.ndiags;
-    View<int> off(A.offsets, A.ndiags, false);
+    if (total == 0) return;
+    const int* off = mirror(A.offsets, (size_t)A.ndiags);
+    const double* va = mirror(A.values, total);
+    if (kind(A.values) == 2 && first_gpu_use(A.values)) prefetch_traced(A.values, sizeof(double) * total);
     // The reference guards columns with j < nrow (src/mat_vec.cpp:140), so it reads x[0..nrow).
-    View<double> va(A.values, total, false), xv(x.values, x.size, false), yv(y.values, A.nrow, true);
+    View<double> xv(x.values, x.size, false), yv(y.values, A.nrow, true);
     ok(thsp_dia_spmv_f64(A.nrow, A.ncol, A.ndiags, off, va, xv, yv, nullptr), "DIA SpMV");
     sync();
     yv.commit();
@@ -98,7 +133,7 @@ void DIAMatrixMatVector(const DIAMatrix& A, const Vector& x, Vector& y)
 namespace {
 
 const int kRepeats = 50;  // NTESTS in the reference (src/mat_vec.cpp:201,270,339,400,455)
-bool g_driver_syncs = false;
+thread_local bool g_driver_syncs = false;   // set while a *Numa driver on THIS thread launches on all devices and syncs once
 
 int gpu_count_for(int nthreads)
 {
@@ -193,21 +228,36 @@ void* COOMatrixMatVectorNumaThread(void* args)
 }
 
 namespace {
-struct CscExtra {
-    int nrow;
-};
-std::vector<CscExtra> g_csc_extra;  // nrow per block, indexed by core_ind (NumaNode4CSC has no field for it)
-struct DiaExtra {
-    int nrow_total;
-};
-std::vector<DiaExtra> g_dia_extra;
+// What the reference's node structs have no field for (include/numa_node.h is kept field-compatible): the row count of
+// the whole matrix, per node, filled by the *Numa drivers below.  Keyed by the node's address and locked, so that the
+// exported thread entries stay usable on their own and from several host threads.
+std::mutex g_extra_mu;
+std::unordered_map<const void*, int> g_rows_total;
+void set_rows_total(const void* node, int n)
+{
+    std::lock_guard<std::mutex> lk(g_extra_mu);
+    g_rows_total[node] = n;
+}
+void drop_rows_total(const void* node)
+{
+    std::lock_guard<std::mutex> lk(g_extra_mu);
+    g_rows_total.erase(node);
+}
+int rows_total(const void* node, int fallback)
+{
+    std::lock_guard<std::mutex> lk(g_extra_mu);
+    auto it = g_rows_total.find(node);
+    return it == g_rows_total.end() ? fallback : it->second;
+}
 }  // namespace
 
 void* CSCMatrixMatVectorNumaThread(void* args)
 {
     NumaNode4CSC* pn = static_cast<NumaNode4CSC*>(args);
     use(pn->alloc);
-    const int nrow = pn->core_ind < (int)g_csc_extra.size() ? g_csc_extra[pn->core_ind].nrow : 0;
+    // A node built by the caller (the reference's thread body needs no row count, src/mat_vec.cpp:553-560): the kernel
+    // only uses the count to clamp its shared-memory window, so "unknown" = no clamp.
+    const int nrow = rows_total(pn, 0x7fffffff);
     ok(thsp_csc_spmv_f64(nrow, pn->cols_per_node, pn->nnz, pn->sub_col_ptr, pn->sub_row_ind, pn->sub_values, pn->X, pn->Y, nullptr),
        "CSC block SpMV");
     if (!g_driver_syncs) ok(thsp_device_sync(), "device synchronise");
@@ -218,7 +268,8 @@ void* DIAMatrixMatVectorNumaThread(void* args)
 {
     NumaNode4DIA* pn = static_cast<NumaNode4DIA*>(args);
     use(pn->alloc);
-    const int total = pn->core_ind < (int)g_dia_extra.size() ? g_dia_extra[pn->core_ind].nrow_total : pn->rows_per_node;
+    // caller-built node: the reference's own (block-local) column guard, src/mat_vec.cpp:597-598
+    const int total = rows_total(pn, pn->start_row + pn->rows_per_node);
     ok(thsp_dia_spmv_rows_f64(pn->start_row, pn->rows_per_node, total, pn->ndiags, pn->offsets, pn->values, pn->X, pn->Y, nullptr),
        "DIA block SpMV");
     if (!g_driver_syncs) ok(thsp_device_sync(), "device synchronise");
@@ -366,11 +417,11 @@ void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int 
     std::vector<NumaNode4CSC> p(G);
     std::vector<int> cp_host((size_t)A.ncol + 1);
     copy_bytes(cp_host.data(), A.col_ptr, sizeof(int) * ((size_t)A.ncol + 1));
-    g_csc_extra.assign(G, CscExtra{A.nrow});
     for (int i = 0; i < G; ++i) {
         int64_t start = 0, count = 0;
         ok(thsp_partition_rows(A.ncol, G, i, &start, &count), "column partition");
         NumaNode4CSC& b = p[i];
+        set_rows_total(&b, A.nrow);
         b.alloc = i;
         b.core_ind = i;
         b.start_col = (int)start;
@@ -402,6 +453,7 @@ void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int 
     for (int i = 0; i < G; ++i) {
         use(i);
         thsp_free(p[i].sub_col_ptr); thsp_free(p[i].sub_row_ind); thsp_free(p[i].sub_values); thsp_free(p[i].X); thsp_free(p[i].Y);
+        drop_rows_total(&p[i]);
     }
     use(dev0);
 }
@@ -413,11 +465,11 @@ void DIAMatrixMatVectorNuma(const DIAMatrix& A, const Vector& x, Vector& y, int 
     int dev0 = 0;
     thsp_get_device(&dev0);
     std::vector<NumaNode4DIA> p(G);
-    g_dia_extra.assign(G, DiaExtra{A.nrow});
     for (int i = 0; i < G; ++i) {
         int64_t start = 0, count = 0;
         ok(thsp_partition_rows(A.nrow, G, i, &start, &count), "row partition");
         NumaNode4DIA& b = p[i];
+        set_rows_total(&b, A.nrow);
         b.alloc = i;
         b.core_ind = i;
         b.start_row = (int)start;
@@ -438,6 +490,7 @@ void DIAMatrixMatVectorNuma(const DIAMatrix& A, const Vector& x, Vector& y, int 
         use(i);
         copy_bytes(y.values + p[i].start_row, p[i].Y, sizeof(double) * (size_t)p[i].rows_per_node);  // as the reference does (:472-477)
         thsp_free(p[i].offsets); thsp_free(p[i].values); thsp_free(p[i].X); thsp_free(p[i].Y);
+        drop_rows_total(&p[i]);
     }
     use(dev0);
 }

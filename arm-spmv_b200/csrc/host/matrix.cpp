@@ -12,15 +12,17 @@ using namespace thsp_host;
 
 namespace {
 
-// Number of row==col entries the reference would have packed into `diagonal` (<= nrow kept).
+// Device-usable arrays of a COO matrix: in place when the library owns them, else through the device mirror that the
+// first conversion uploads and the next ones (CSR, CSC, ELL of the same matrix: main.cpp:38-41) find again.
 struct CooArrays {
-    View<int> ri, ci;
-    View<double> va;
-    CooArrays(const COOMatrix& A) : ri(A.row_ind, A.nnz, false), ci(A.col_ind, A.nnz, false), va(A.values, A.nnz, false) {}
+    const int *ri, *ci;
+    const double* va;
+    CooArrays(const COOMatrix& A) : ri(mirror(A.row_ind, A.nnz)), ci(mirror(A.col_ind, A.nnz)), va(mirror(A.values, A.nnz)) {}
 };
 
 void csr_from_coo(CSRMatrix& B, const COOMatrix& A)
 {
+    Trace tr("CSRMatrix(COOMatrix)");
     B.nrow = A.nrow;
     B.ncol = A.ncol;
     B.row_ptr = alloc<int>((size_t)A.nrow + 1);
@@ -35,6 +37,7 @@ void csr_from_coo(CSRMatrix& B, const COOMatrix& A)
 
 void csc_from_coo(CSCMatrix& C, const COOMatrix& A)
 {
+    Trace tr("CSCMatrix(COOMatrix)");
     C.nrow = A.nrow;
     C.ncol = A.ncol;
     C.col_ptr = alloc<int>((size_t)A.ncol + 1);
@@ -47,6 +50,7 @@ void csc_from_coo(CSCMatrix& C, const COOMatrix& A)
 
 void ell_from_coo(ELLMatrix& D, const COOMatrix& A)
 {
+    Trace tr("ELLMatrix(COOMatrix)");
     D.nrow = A.nrow;
     D.ncol = A.ncol;
     D.nnz = A.nnz;
@@ -65,12 +69,14 @@ void ell_from_coo(ELLMatrix& D, const COOMatrix& A)
 
 void dia_from_csr(DIAMatrix& E, const CSRMatrix& A)
 {
+    Trace tr("DIAMatrix(CSRMatrix)");
     const int nnz = A.nrow > 0 ? peek_int(A.row_ptr + A.nrow) : 0;
     E.nnz = nnz;
     E.nrow = A.nrow;
     E.ncol = A.ncol;
-    View<int> rp(A.row_ptr, (size_t)A.nrow + 1, false), ci(A.col_ind, nnz, false);
-    View<double> va(A.values, nnz, false);
+    const int* rp = mirror(A.row_ptr, (size_t)A.nrow + 1);
+    const int* ci = mirror(A.col_ind, (size_t)nnz);
+    const double* va = mirror(A.values, (size_t)nnz);
     int nd = 0;
     ok(thsp_csr2dia_offsets(A.nrow, A.ncol, rp, ci, &nd, nullptr, 0, nullptr), "CSR -> DIA (count)");
     E.ndiags = nd;

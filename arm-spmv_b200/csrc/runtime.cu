@@ -172,7 +172,7 @@ int thsp_pointer_kind(const void* ptr)
     memset(&at, 0, sizeof(at));
     if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
         cudaGetLastError();
-        return 0;
+        return -1;   // the runtime could not say (sticky error, shutting down): NOT "plain host memory"
     }
     switch (at.type) {
         case cudaMemoryTypeDevice: return 1;

@@ -305,6 +305,7 @@ def COOMatrixRead(path: str, device=None) -> COOMatrix:
     """COOMatrixRead (src/data_io.cpp:45-105) with the entry loop (:83-88) on the GPU (thsp_mtx_parse_coo)."""
     rows, cols, nz, body = mtx_split(path)
     dev = _dev(device)
+    check(load().thsp_prepare_conversions(rows, cols, nz, current_stream()))   # as the C++ reader does (csrc/host/data_io.cpp)
     ri = torch.empty(nz, dtype=I32, device=dev)
     ci = torch.empty(nz, dtype=I32, device=dev)
     va = torch.empty(nz, dtype=F64, device=dev)

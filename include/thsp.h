@@ -58,7 +58,8 @@ THSP_API int thsp_host_register(void* ptr, size_t bytes);
 THSP_API int thsp_host_unregister(void* ptr);
 THSP_API int thsp_free(void* ptr);
 THSP_API int thsp_free_host(void* ptr);
-/* 0 = plain host (or unknown), 1 = device, 2 = managed, 3 = pinned host */
+/* 0 = plain host, 1 = device, 2 = managed, 3 = pinned host, -1 = the CUDA runtime could not classify the pointer
+ * (a sticky error, or the runtime is shutting down) - callers must not treat that as host memory */
 THSP_API int thsp_pointer_kind(const void* ptr);
 THSP_API int thsp_memcpy_h2d(void* dst, const void* src_host, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_memcpy_d2h(void* dst_host, const void* src, size_t bytes, thsp_stream_t stream);
@@ -106,6 +107,12 @@ THSP_API int thsp_csr_plan_create(thsp_csr_plan** plan, int nrow, int ncol, int 
                                   const int* col_ind, const void* val, int value_bytes /* 8 or 4 */,
                                   thsp_stream_t stream);
 THSP_API int thsp_csr_plan_destroy(thsp_csr_plan* plan);
+/* A plan remembers the arrays' addresses, the entry count and the kernel chosen from the row lengths - nothing else
+ * derived from their contents.  If a caller rewrites row_ptr in place so that row_ptr[nrow] changes, the kernels whose
+ * launch shape depends on the entry count (stream, merge) notice it on the device, write nothing and raise a flag:
+ * after synchronising the stream, *stale = 1 says "destroy this plan, create a new one, repeat the product"; the flag is
+ * cleared by the call.  The C++ classes do exactly that (csrc/host/mat_vec.cpp). */
+THSP_API int thsp_csr_plan_stale(const thsp_csr_plan* plan, int* stale);
 THSP_API int thsp_csr_plan_kernel(const thsp_csr_plan* plan, int* kernel, int* lanes);
 THSP_API int thsp_csr_plan_set_kernel(thsp_csr_plan* plan, int kernel, int lanes);
 /* Tuning knobs of the STREAM kernel (0 keeps the current value): warps per CTA, ring depth per
@@ -189,6 +196,11 @@ THSP_API int thsp_csr2dia_offsets(int nrow, int ncol, const int* row_ptr, const 
                                   int* offsets, int offsets_capacity, thsp_stream_t stream);
 THSP_API int thsp_csr2dia_fill(int nrow, int ncol, const int* row_ptr, const int* col_ind, const double* val,
                                int ndiags, const int* offsets, double* values, thsp_stream_t stream);
+/* Called by the reader once the sizes are known (COOMatrixRead, src/data_io.cpp:45-105): grows the library's scratch
+ * to what conversions of an nrow x ncol matrix with nnz entries need and runs each conversion once on a 96-entry matrix,
+ * so that the constructors that follow - main.cpp:38-41 calls each exactly once - run at their steady-state speed instead
+ * of paying for allocations and first-launch kernel loading.  Optional: everything works without it.  Synchronous. */
+THSP_API int thsp_prepare_conversions(int nrow, int ncol, int nnz, thsp_stream_t stream);
 /* row_ptr scan on its own: exclusive prefix sum of n int32 counts into out[0..n] (out[n]=total). */
 THSP_API int thsp_exclusive_scan_i32(int n, const int* counts, int* out, thsp_stream_t stream);
 

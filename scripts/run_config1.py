@@ -33,7 +33,9 @@ for exe, label in ((os.path.join(ROOT, "bin", "main"), "bin/main = reference mai
     if not os.path.exists(exe):
         print("missing", exe); continue
     t0 = time.time()
-    r = subprocess.run([exe, path, threads], capture_output=True, text=True)
+    r = subprocess.run([exe, path, threads], capture_output=True, text=True, env=dict(os.environ, THSP_TRACE=os.environ.get("THSP_TRACE", "0")))
     print(f"--- {label}: argv = {path} {threads}, exit {r.returncode}, wall {time.time() - t0:.1f} s")
     print("\n".join(l for l in r.stdout.splitlines() if l.startswith("###")))
     if r.returncode != 0: print(r.stderr[-1000:])
+    if os.environ.get("THSP_TRACE") == "1" and "bin/main" in exe:
+        print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[thsp]"))[:6000])

@@ -69,3 +69,20 @@ def test_reference_main_runs_on_the_gpu_library(tmp_path):
         for kind in ("CPU", "NUMA"):   # the reference's label for its un-partitioned loop is "CPU"
             m = re.search(rf"### {fmt} {kind} GFLOPS = ([0-9.eE+-]+|inf|nan)", r.stdout)
             assert m, f"missing '### {fmt} {kind} GFLOPS' in:\n{r.stdout}"
+
+
+def test_adopted_arrays_are_mirrored_once_and_never_stale(tmp_path):
+    """bin/adopt_check: CSRMatrix / COOMatrix / Vector built on caller new[] arrays (the adopting constructors,
+    src/matrix.cpp:12-15,88-91).  Every product equals the host loop; THSP_TRACE shows the matrix arrays uploaded by the
+    first product only, again after the caller refilled them, and the plan rebuilt after row_ptr[nrow] changed."""
+    exe = os.path.join(ROOT, "bin", "adopt_check")
+    assert os.path.exists(exe), "bin/adopt_check missing: run __graft_entry__.build()"
+    r = subprocess.run([exe, "300000"], capture_output=True, text=True, timeout=300, env=dict(os.environ, THSP_TRACE="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ALL OK" in r.stdout and "MISMATCH" not in r.stdout
+    calls = r.stderr.split("[adopt] call ")
+    uploads = [c.count("device mirror of") for c in calls[1:]]
+    assert uploads[0] == 3, uploads           # row_ptr, col_ind, values
+    assert uploads[1] == 0 and uploads[2] == 0, uploads   # found again; only x and y move
+    assert uploads[3] >= 1, uploads           # values refilled: uploaded again
+    assert uploads[4] >= 1, uploads           # row_ptr rewritten: uploaded again, plan rebuilt for the new entry count

@@ -332,8 +332,8 @@ def test_ell_fp32(thsp, cuda, oracle, nrow_pad):
     y0 = oracle.gen_vector(nrow, 8).astype(np.float32)
     v32 = eva.astype(np.float32)
     want = oracle.ell_spmv_f32(nrow, k, eco, v32, x, y0)
-    y = dev(y0)
-    check(load().thsp_ell_spmv_f32(nrow, ncol, k, ptr(dev(eco)), ptr(dev(v32)), ptr(dev(x)), ptr(y), current_stream()))
+    y, d_col, d_val, d_x = dev(y0), dev(eco), dev(v32), dev(x)   # named: the tensors must outlive the launch
+    check(load().thsp_ell_spmv_f32(nrow, ncol, k, ptr(d_col), ptr(d_val), ptr(d_x), ptr(y), current_stream()))
     assert_bits(host(y), want, "ELL fp32")
     ref64 = oracle.ell_spmv(nrow, ncol, k, eco, v32.astype(np.float64), x.astype(np.float64), y0.astype(np.float64))
     scale = row_scale_coo(nrow, ri, ci, va.astype(np.float32).astype(np.float64), x.astype(np.float64))
