@@ -25,6 +25,8 @@
 
 namespace thsp {
 
+void warm_stale_page();   // csr_spmv.cu
+
 // =========================================================== exclusive scan (int32) =======
 static constexpr int kScanThreads = 256;
 static constexpr int kScanItems = 4;   // diag_flags() loads them as one int4
@@ -1072,6 +1074,7 @@ int thsp_csr2dia_fill(int nrow, int ncol, const int* row_ptr, const int* col_ind
 int thsp_prepare_conversions(int nrow, int ncol, int nnz, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
+    warm_stale_page();
     cudaStream_t s = as_stream(stream);
     const int nb = div_up(std::max(nnz, 1), kScanTile);
     if (!scratch(sizeof(int) * 4, 1)) return 1;

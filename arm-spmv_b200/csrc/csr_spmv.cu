@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -102,7 +103,6 @@ struct StreamCfg {
     int warps;   // per CTA
     int stages;  // ring depth per warp
     int chunk;   // CH
-    int tile_stride = 1;   // TS: tiles per grid line of a matrix from a regular grid (1 = plain round-robin)
 };
 
 template <typename V>
@@ -118,7 +118,7 @@ template <typename V>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
-                      V* __restrict__ tile_ss, int TS, int* __restrict__ stale)
+                      V* __restrict__ tile_ss, int* __restrict__ stale)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -149,28 +149,11 @@ __global__ void __launch_bounds__(768, 1)
     const int num_tiles = (nrow + 31) >> 5;
     const int nnz_al = nnz & ~3;
     const uint64_t pol = policy_evict_first();
-    // Which tile a warp takes at its q-th step.  The tiles are seen as lines of TS tiles; step B = q * grid + CTA of the
-    // whole grid is the x-position B % TS of line group B / TS, and the W warps of the CTA take that position in W
-    // CONSECUTIVE lines.  On a matrix from a regular grid whose rows lie TS tiles (one grid line) apart, the warps of a
-    // CTA then gather from x-lines they share (a row reads the lines above and below its own) and L1 serves what L2
-    // served before: profiles/r02_slab_*.  TS = 1 is the plain round-robin (tile = B * W + warp) for everything else.
-    // Steps that fall off the end of the matrix are skipped; num_tiles = done.
-    auto tile_of = [&](int& q) -> int {
-        while (true) {
-            const long long B = (long long)q * gridDim.x + blockIdx.x;
-            const long long lg = B / TS, xt = B - lg * TS;
-            if (lg * W * TS >= num_tiles) return num_tiles;
-            const long long t = (lg * W + warp) * TS + xt;
-            if (t < num_tiles) return (int)t;
-            ++q;
-        }
-    };
+    const int GW = gridDim.x * W;
+    const int gw = blockIdx.x * W + warp;
 
     // ---- producer cursor (warp-uniform): runs S chunks ahead of the consumer --------------
-    int p_q = 0, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
-    int p_tile = tile_of(p_q);
-    int n_q = p_q + 1;
-    int n_tile = p_tile < num_tiles ? tile_of(n_q) : num_tiles;   // the tile after p_tile
+    int p_tile = gw, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
     bool p_open = false;
     int pf_rs = 0, pf_re = 0;  // row bounds of p_tile, fetched one step ahead
     if (p_tile < num_tiles) {
@@ -179,8 +162,7 @@ __global__ void __launch_bounds__(768, 1)
         pf_re = __ldg(row_ptr + min(r + 1, nrow));
     }
     // ---- consumer cursor ------------------------------------------------------------------
-    int c_q = 0, c_slot = 0, c_chunk = 0, c_nch = 1, c_al = 0, c_te = 0, c_stage = 0;
-    int c_tile = tile_of(c_q);
+    int c_tile = gw, c_slot = 0, c_chunk = 0, c_nch = 1, c_al = 0, c_te = 0, c_stage = 0;
     unsigned c_parity = 0;
     int rs = 0, re = 0;
     V sum = V(0), yold = V(0);
@@ -199,8 +181,9 @@ __global__ void __launch_bounds__(768, 1)
                 p_nch = max(1, (p_te - p_al + CH - 1) / CH);
                 p_chunk = 0;
                 p_open = true;
-                if (n_tile < num_tiles) {   // bounds of the tile after this one
-                    const int r = n_tile * 32 + lane;
+                const int nt = p_tile + GW;  // bounds of the tile after this one
+                if (nt < num_tiles) {
+                    const int r = nt * 32 + lane;
                     pf_rs = __ldg(row_ptr + min(r, nrow));
                     pf_re = __ldg(row_ptr + min(r + 1, nrow));
                 }
@@ -228,11 +211,7 @@ __global__ void __launch_bounds__(768, 1)
             }
             p_stage = (p_stage + 1 == S) ? 0 : p_stage + 1;
             if (++p_chunk == p_nch) {
-                p_tile = n_tile;
-                if (n_tile < num_tiles) {
-                    ++n_q;
-                    n_tile = tile_of(n_q);
-                }
+                p_tile += GW;
                 p_slot = (p_slot + 1 == S) ? 0 : p_slot + 1;
                 p_open = false;
             }
@@ -290,8 +269,7 @@ __global__ void __launch_bounds__(768, 1)
                 for (int o = 16; o > 0; o >>= 1) q = add_rn(q, __shfl_xor_sync(full, q, o));
                 if (lane == 0) tile_ss[c_tile] = q;
             }
-            ++c_q;
-            c_tile = tile_of(c_q);
+            c_tile += GW;
             c_slot = (c_slot + 1 == S) ? 0 : c_slot + 1;
             c_chunk = 0;
         }
@@ -319,12 +297,17 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    const int ts = cfg.tile_stride >= 1 && (int64_t)cfg.tile_stride * cfg.warps <= num_tiles ? cfg.tile_stride : 1;
-    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, ts, stale);
+    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale);
     THSP_LAUNCH_CHECK();
     return 0;
 }
 
+// Tried and dropped in round 2 (profiles/r02_slab_tile_stride.txt): on the 512^3 slab of one rank the kernel runs 6 %
+// slower than on 256^3 (0.936 vs 0.882 ms, same rows and entries) and ncu shows why - L1 serves 69 % of the x gathers
+// instead of 77 %, because a CTA's 20 consecutive tiles cover 1.25 grid lines of 512 instead of 2.5 of 256.  Handing
+// the warps of a CTA tiles one grid line apart (they then gather from lines they share) left the L1 hit rate at 69.5 %:
+// with 200 KB of the SM's array taken by the stages, ~30 KB of L1 do not hold a line until the neighbouring warp comes
+// by, and the index arithmetic cost 4-10 %.
 // Default shape: one 32-row tile fits one stage, and as many warps as shared memory and the
 // 768-thread launch bound allow.  Measured on B200 (profiles/): the kernel is bound by the
 // latency of a tile's load -> gather -> sum chain, so warps in flight matter more than ring
@@ -693,6 +676,33 @@ struct HostPipe {
     std::vector<cudaEvent_t> t_in, t_k0, t_k1, t_out;
 };
 
+// Stale flags live in ONE pinned, device-mapped page per process: cudaHostAlloc costs 1-2 ms, which as a per-plan cost
+// landed inside main.cpp's 50-call timing loop (the first call creates the plan) and halved "### CSR CPU GFLOPS".
+static int* stale_slot_acquire()
+{
+    static std::mutex mu;
+    static int* page = nullptr;
+    static std::vector<int> free_slots;
+    static int next = 0;
+    static bool failed = false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!page && !failed) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&page), sizeof(int) * 1024, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            page = nullptr;
+            failed = true;
+        } else {
+            memset(page, 0, sizeof(int) * 1024);
+        }
+    }
+    if (!page) return nullptr;
+    return next < 1024 ? page + next++ : nullptr;   // a process that makes more than 1024 plans runs the later ones unchecked
+}
+
+namespace thsp {
+void warm_stale_page() { stale_slot_acquire(); }   // thsp_prepare_conversions: the page exists before the first plan is timed
+}
+
 struct thsp_csr_plan {
     HostPipe* pipe = nullptr;
     // Nothing here is derived from the contents of the arrays except nnz, the histogram and the kernel choice made from
@@ -763,44 +773,6 @@ static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStre
                        static_cast<const V*>(p->val), x, y, acc, s);
 }
 
-// Rows of a matrix from a regular grid read the grid lines above and below their own: the smallest column offset
-// beyond the row's own neighbours is the length of a grid line.  Three sample rows must agree on it; the stream kernel
-// then lets the warps of a CTA work one grid line apart (tile_of in csr_stream_kernel).  1 = no such structure.
-static int detect_tile_stride(int nrow, const int* row_ptr, const int* col_ind, cudaStream_t s)
-{
-    if (const char* e = getenv("THSP_TILE_STRIDE")) {
-        const int v = atoi(e);
-        if (v >= 1) return v;
-    }
-    if (nrow < 4096) return 1;
-    int agreed = 0;
-    for (int k = 1; k <= 3; ++k) {
-        const int r = (int)((int64_t)nrow * k / 4);
-        int b[2] = {0, 0};
-        if (cudaMemcpyAsync(b, row_ptr + r, sizeof(b), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        const int len = b[1] - b[0];
-        if (len < 3 || len > 128) return 1;
-        int cols[128];
-        if (cudaMemcpyAsync(cols, col_ind + b[0], sizeof(int) * (size_t)len, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-            cudaStreamSynchronize(s) != cudaSuccess) {
-            cudaGetLastError();
-            return 1;
-        }
-        int d = 0;
-        for (int i = 0; i < len; ++i) {
-            const int off = cols[i] - r;
-            if (off > 1 && (d == 0 || off < d)) d = off;
-        }
-        if (d == 0 || (agreed && d != agreed)) return 1;
-        agreed = d;
-    }
-    const int ts = (agreed + 16) / 32;
-    return ts >= 2 && ts <= 4096 ? ts : 1;
-}
-
 extern "C" {
 
 int thsp_csr_spmv_kernel_f64(int kernel, int lanes, int nrow, int ncol, int nnz, const int* row_ptr, const int* col_ind,
@@ -841,12 +813,7 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
     p->ctas = sm_count();
     for (int i = 0; i < 32; ++i) p->hist[i] = 0;
     p->max_len = 0;
-    if (cudaHostAlloc(reinterpret_cast<void**>(&p->stale), sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
-        cudaGetLastError();
-        p->stale = nullptr;   // no flag, no check: the plan still works
-    } else {
-        *p->stale = 0;
-    }
+    p->stale = stale_slot_acquire();   // nullptr = no flag, no check: the plan still works
     if (nrow > 0) {
         unsigned long long* dh = static_cast<unsigned long long*>(scratch(33 * sizeof(unsigned long long), 4));
         if (!dh) { delete p; return 1; }
@@ -882,7 +849,6 @@ int thsp_csr_plan_create(thsp_csr_plan** out, int nrow, int ncol, int nnz, const
         p->lanes = lanes_for_mean(mean);
     }
     p->stream_cfg = value_bytes == 8 ? default_stream_cfg<double>(nrow, nnz) : default_stream_cfg<float>(nrow, nnz);
-    if (p->kernel == THSP_CSR_STREAM) p->stream_cfg.tile_stride = detect_tile_stride(nrow, row_ptr, col_ind, s);
     *out = p;
     return 0;
 }
@@ -907,7 +873,6 @@ static void drop_host_pipe(thsp_csr_plan* plan)
 int thsp_csr_plan_destroy(thsp_csr_plan* plan)
 {
     if (plan) drop_host_pipe(plan);
-    if (plan && plan->stale) cudaFreeHost(plan->stale);
     delete plan;
     return 0;
 }

@@ -78,9 +78,9 @@ void COOMatrixRead(const char* filename, COOMatrix& A)
     int rows = 0, cols = 0, nz = 0;
     if (mm_read_mtx_crd_size(fp, &rows, &cols, &nz) != 0) exit(1);
     printf("\tAllocating memory for matrix\n");
-    int* ri = alloc<int>(nz);
-    int* ci = alloc<int>(nz);
-    double* va = alloc<double>(nz);
+    int* ri = alloc_matrix<int>(nz);
+    int* ci = alloc_matrix<int>(nz);
+    double* va = alloc_matrix<double>(nz);
     printf("\tReading matrix entries from file\n");
     bool on_gpu = false;
     const long pos = ftell(fp);

@@ -309,10 +309,21 @@ void forget_plans(const void* a)
     }
 }
 
-Trace::Trace(const char* what) : what_(what), t0_(trace_on() ? now_ms() : 0.0) {}
+static double trace_origin()
+{
+    static const double t = now_ms();
+    return t;
+}
+Trace::Trace(const char* what) : what_(what), t0_(0.0)
+{
+    if (trace_on()) {
+        trace_origin();
+        t0_ = now_ms();
+    }
+}
 Trace::~Trace()
 {
-    if (trace_on()) fprintf(stderr, "[thsp] %-28s %10.3f ms\n", what_, now_ms() - t0_);
+    if (trace_on()) fprintf(stderr, "[thsp] at %9.1f ms  %-28s %10.3f ms\n", t0_ - trace_origin(), what_, now_ms() - t0_);
 }
 
 }  // namespace thsp_host

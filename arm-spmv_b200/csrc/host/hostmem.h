@@ -31,6 +31,16 @@ inline T* alloc(size_t n)
     return static_cast<T*>(alloc_managed_bytes((n ? n : 1) * sizeof(T)));
 }
 
+// Matrix arrays: written once (by a conversion kernel, the GPU parser or the scanf loop), then only read - by kernels and,
+// in main.cpp:46-52, by a host loop in between.  Read-mostly advice lets both processors keep a copy.
+template <class T>
+inline T* alloc_matrix(size_t n)
+{
+    T* p = alloc<T>(n);
+    ok(thsp_advise_read_mostly(p, (n ? n : 1) * sizeof(T)), "read-mostly advice");
+    return p;
+}
+
 // 0 plain host, 1 device, 2 managed, 3 pinned host, -1 the CUDA runtime could not say.  Library-owned arrays are
 // answered from the record; other pointers are asked once and remembered until they are released or invalidated.
 int kind(const void* p);

@@ -279,6 +279,7 @@ void* DIAMatrixMatVectorNumaThread(void* args)
 // ---- CSR: row blocks, row_ptr rebased (src/mat_vec.cpp:230-297) --------------------------------
 void CSRMatrixMatVectorNuma(const CSRMatrix& A, const Vector& x, Vector& y, int nthreads)
 {
+    Trace tr("CSRMatrixMatVectorNuma");
     const int G = gpu_count_for(nthreads);
     int dev0 = 0;
     thsp_get_device(&dev0);
@@ -323,6 +324,7 @@ void CSRMatrixMatVectorNuma(const CSRMatrix& A, const Vector& x, Vector& y, int 
 // ---- ELL: row blocks of the column-major slab (src/mat_vec.cpp:368-426) ------------------------
 void ELLMatrixMatVectorNuma(const ELLMatrix& A, const Vector& x, Vector& y, int nthreads)
 {
+    Trace tr("ELLMatrixMatVectorNuma");
     const int G = gpu_count_for(nthreads);
     int dev0 = 0;
     thsp_get_device(&dev0);
@@ -368,6 +370,7 @@ void ELLMatrixMatVectorNuma(const ELLMatrix& A, const Vector& x, Vector& y, int 
 //  the entry stream works for any order)
 void COOMatrixMatVectorNuma(const COOMatrix& A, const Vector& x, Vector& y, int nthreads)
 {
+    Trace tr("COOMatrixMatVectorNuma");
     const int G = gpu_count_for(nthreads);
     int dev0 = 0;
     thsp_get_device(&dev0);
@@ -411,6 +414,7 @@ void COOMatrixMatVectorNuma(const COOMatrix& A, const Vector& x, Vector& y, int 
 // ---- CSC: column blocks, private full-length y (src/mat_vec.cpp:299-366), reduced at the end ----
 void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int nthreads)
 {
+    Trace tr("CSCMatrixMatVectorNuma");
     const int G = gpu_count_for(nthreads);
     int dev0 = 0;
     thsp_get_device(&dev0);
@@ -461,6 +465,7 @@ void CSCMatrixMatVectorNuma(const CSCMatrix& A, const Vector& x, Vector& y, int 
 // ---- DIA: row blocks of the row-major diagonals (src/mat_vec.cpp:428-484) ----------------------
 void DIAMatrixMatVectorNuma(const DIAMatrix& A, const Vector& x, Vector& y, int nthreads)
 {
+    Trace tr("DIAMatrixMatVectorNuma");
     const int G = gpu_count_for(nthreads);
     int dev0 = 0;
     thsp_get_device(&dev0);

@@ -25,10 +25,10 @@ void csr_from_coo(CSRMatrix& B, const COOMatrix& A)
     Trace tr("CSRMatrix(COOMatrix)");
     B.nrow = A.nrow;
     B.ncol = A.ncol;
-    B.row_ptr = alloc<int>((size_t)A.nrow + 1);
-    B.col_ind = alloc<int>(A.nnz);
-    B.values = alloc<double>(A.nnz);
-    B.diagonal = alloc<double>(A.nrow);
+    B.row_ptr = alloc_matrix<int>((size_t)A.nrow + 1);
+    B.col_ind = alloc_matrix<int>(A.nnz);
+    B.values = alloc_matrix<double>(A.nnz);
+    B.diagonal = alloc_matrix<double>(A.nrow);
     CooArrays in(A);
     ok(thsp_coo2csr(A.nrow, A.ncol, A.nnz, in.ri, in.ci, in.va, B.row_ptr, B.col_ind, B.values, B.diagonal, nullptr, nullptr),
        "COO -> CSR");
@@ -40,9 +40,9 @@ void csc_from_coo(CSCMatrix& C, const COOMatrix& A)
     Trace tr("CSCMatrix(COOMatrix)");
     C.nrow = A.nrow;
     C.ncol = A.ncol;
-    C.col_ptr = alloc<int>((size_t)A.ncol + 1);
-    C.row_ind = alloc<int>(A.nnz);
-    C.values = alloc<double>(A.nnz);
+    C.col_ptr = alloc_matrix<int>((size_t)A.ncol + 1);
+    C.row_ind = alloc_matrix<int>(A.nnz);
+    C.values = alloc_matrix<double>(A.nnz);
     CooArrays in(A);
     ok(thsp_coo2csc(A.nrow, A.ncol, A.nnz, in.ri, in.ci, in.va, C.col_ptr, C.row_ind, C.values, nullptr), "COO -> CSC");
     sync();
@@ -59,9 +59,9 @@ void ell_from_coo(ELLMatrix& D, const COOMatrix& A)
     ok(thsp_coo2ell_prepare(A.nrow, A.ncol, A.nnz, in.ri, in.ci, in.va, &width, nullptr), "ELL width");
     D.nonzeros_in_row = width;
     const size_t total = (size_t)A.nrow * (size_t)width;
-    D.col_ind = alloc<int>(total);
-    D.values = alloc<double>(total);
-    D.diagonal = alloc<double>(A.nrow);
+    D.col_ind = alloc_matrix<int>(total);
+    D.values = alloc_matrix<double>(total);
+    D.diagonal = alloc_matrix<double>(A.nrow);
     ok(thsp_coo2ell(A.nrow, A.ncol, A.nnz, in.ri, in.ci, in.va, width, D.col_ind, D.values, D.diagonal, nullptr, nullptr),
        "COO -> ELL");
     sync();
@@ -80,8 +80,8 @@ void dia_from_csr(DIAMatrix& E, const CSRMatrix& A)
     int nd = 0;
     ok(thsp_csr2dia_offsets(A.nrow, A.ncol, rp, ci, &nd, nullptr, 0, nullptr), "CSR -> DIA (count)");
     E.ndiags = nd;
-    E.offsets = alloc<int>(nd);
-    E.values = alloc<double>((size_t)A.nrow * (size_t)nd);
+    E.offsets = alloc_matrix<int>(nd);
+    E.values = alloc_matrix<double>((size_t)A.nrow * (size_t)nd);
     ok(thsp_csr2dia_offsets(A.nrow, A.ncol, rp, ci, &nd, E.offsets, nd, nullptr), "CSR -> DIA (offsets)");
     ok(thsp_csr2dia_fill(A.nrow, A.ncol, rp, ci, va, nd, E.offsets, E.values, nullptr), "CSR -> DIA (fill)");
     sync();
@@ -95,7 +95,7 @@ COOMatrix::COOMatrix() : nrow(0), ncol(0), nnz(0), row_ind(nullptr), col_ind(nul
 COOMatrix::COOMatrix(int n, int m, int nz, int* ri, int* ci, double* va) : nrow(n), ncol(m), nnz(nz), row_ind(ri), col_ind(ci), values(va) {}
 
 COOMatrix::COOMatrix(const COOMatrix& A)
-    : nrow(A.nrow), ncol(A.ncol), nnz(A.nnz), row_ind(alloc<int>(A.nnz)), col_ind(alloc<int>(A.nnz)), values(alloc<double>(A.nnz))
+    : nrow(A.nrow), ncol(A.ncol), nnz(A.nnz), row_ind(alloc_matrix<int>(A.nnz)), col_ind(alloc_matrix<int>(A.nnz)), values(alloc_matrix<double>(A.nnz))
 {
     copy(row_ind, A.row_ind, (size_t)nnz);
     copy(col_ind, A.col_ind, (size_t)nnz);
@@ -111,9 +111,9 @@ COOMatrix& COOMatrix::operator=(const COOMatrix& A)
     nrow = A.nrow;
     ncol = A.ncol;
     nnz = A.nnz;
-    row_ind = alloc<int>(nnz);
-    col_ind = alloc<int>(nnz);
-    values = alloc<double>(nnz);
+    row_ind = alloc_matrix<int>(nnz);
+    col_ind = alloc_matrix<int>(nnz);
+    values = alloc_matrix<double>(nnz);
     copy(row_ind, A.row_ind, (size_t)nnz);
     copy(col_ind, A.col_ind, (size_t)nnz);
     copy(values, A.values, (size_t)nnz);
@@ -155,10 +155,10 @@ CSRMatrix& CSRMatrix::operator=(const CSRMatrix& A)
     nrow = A.nrow;
     ncol = A.ncol;
     const int nnz = (A.row_ptr && A.nrow >= 0) ? peek_int(A.row_ptr + A.nrow) : 0;
-    row_ptr = alloc<int>((size_t)nrow + 1);
-    col_ind = alloc<int>(nnz);
-    values = alloc<double>(nnz);
-    diagonal = alloc<double>(nrow);
+    row_ptr = alloc_matrix<int>((size_t)nrow + 1);
+    col_ind = alloc_matrix<int>(nnz);
+    values = alloc_matrix<double>(nnz);
+    diagonal = alloc_matrix<double>(nrow);
     copy(row_ptr, A.row_ptr, (size_t)nrow + 1);
     copy(col_ind, A.col_ind, (size_t)nnz);
     copy(values, A.values, (size_t)nnz);
@@ -201,9 +201,9 @@ CSCMatrix& CSCMatrix::operator=(const CSCMatrix& A)
     nrow = A.nrow;
     ncol = A.ncol;
     const int nnz = A.col_ptr ? peek_int(A.col_ptr + A.ncol) : 0;
-    col_ptr = alloc<int>((size_t)ncol + 1);
-    row_ind = alloc<int>(nnz);
-    values = alloc<double>(nnz);
+    col_ptr = alloc_matrix<int>((size_t)ncol + 1);
+    row_ind = alloc_matrix<int>(nnz);
+    values = alloc_matrix<double>(nnz);
     copy(col_ptr, A.col_ptr, (size_t)ncol + 1);
     copy(row_ind, A.row_ind, (size_t)nnz);
     copy(values, A.values, (size_t)nnz);
@@ -254,9 +254,9 @@ ELLMatrix& ELLMatrix::operator=(const ELLMatrix& A)
     nnz = A.nnz;
     nonzeros_in_row = A.nonzeros_in_row;
     const size_t total = (size_t)nrow * (size_t)nonzeros_in_row;
-    col_ind = alloc<int>(total);
-    values = alloc<double>(total);
-    diagonal = alloc<double>(nrow);
+    col_ind = alloc_matrix<int>(total);
+    values = alloc_matrix<double>(total);
+    diagonal = alloc_matrix<double>(nrow);
     copy(col_ind, A.col_ind, total);
     copy(values, A.values, total);
     if (A.diagonal) copy(diagonal, A.diagonal, (size_t)nrow);
@@ -311,8 +311,8 @@ DIAMatrix& DIAMatrix::operator=(const DIAMatrix& A)
     nrow = A.nrow;
     ncol = A.ncol;
     ndiags = A.ndiags;
-    offsets = alloc<int>(ndiags);
-    values = alloc<double>((size_t)nrow * (size_t)ndiags);
+    offsets = alloc_matrix<int>(ndiags);
+    values = alloc_matrix<double>((size_t)nrow * (size_t)ndiags);
     copy(offsets, A.offsets, (size_t)ndiags);
     copy(values, A.values, (size_t)nrow * (size_t)ndiags);
     return *this;

@@ -53,6 +53,7 @@ void Vector::Fill(double a) const
 
 void Vector::FillRandom() const
 {
+    Trace tr("Vector::FillRandom");
     // Deliberately on the host: the reference's values are the process-wide glibc rand()
     // stream (src/vector.cpp:65-69); drawing it here keeps x identical to the reference's.
     for (int i = 0; i < size; ++i) values[i] = (double)rand() / RAND_MAX;

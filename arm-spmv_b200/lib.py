@@ -54,6 +54,8 @@ def load() -> C.CDLL:
         lib.thsp_stencil27_nnz.restype = C.c_int64
         lib.thsp_stencil27_nnz.argtypes = [C.c_int, C.c_int64, C.c_int64]
         lib.thsp_lap5_nnz.restype = C.c_int64
+        lib.thsp_cg_work_doubles.restype = C.c_int64
+        lib.thsp_cg_work_doubles.argtypes = [C.c_int64]
         _lib = lib
     return _lib
 

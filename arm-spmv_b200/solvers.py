@@ -50,6 +50,65 @@ def cg(A: "H.CSRMatrix", b: "H.Vector", x: "H.Vector", tol: float = 1e-10, maxit
     return it, hist[-1], hist
 
 
+class SymGS:
+    """Symmetric Gauss-Seidel on the GPU (thsp_symgs_*): the smoother the reference's `diagonal` arrays were kept for
+    (include/matrix.h:36,81).  The plan colours the rows once; sweep() does forward + backward, colour by colour."""
+
+    def __init__(self, A: "H.CSRMatrix", diagonal: "H.Vector | None" = None):
+        self.A = A
+        self.diagonal = diagonal if diagonal is not None else csr_diagonal(A)
+        h = C.c_void_p()
+        check(load().thsp_symgs_plan_create(C.byref(h), A.nrow, ptr(A.row_ptr), ptr(A.col_ind), current_stream()))
+        self.plan = h
+        nc, rounds = C.c_int(), C.c_int()
+        check(load().thsp_symgs_plan_info(h, C.byref(nc), C.byref(rounds), None, 0, None, None))
+        self.ncolors, self.rounds = nc.value, rounds.value
+
+    def coloring(self):
+        """(color_ptr [ncolors + 1], perm, color) as numpy arrays (tests: validity of the colouring, the oracle's sweep)."""
+        import numpy as np
+        import torch
+        cp = (C.c_int * (self.ncolors + 1))()
+        perm, color = C.c_void_p(), C.c_void_p()
+        check(load().thsp_symgs_plan_info(self.plan, None, None, cp, self.ncolors + 1, C.byref(perm), C.byref(color)))
+        n = self.A.nrow
+        out = torch.empty(2 * n, dtype=torch.int32, device=self.A.values.device)
+        check(load().thsp_memcpy_d2d(ptr(out), perm, C.c_size_t(4 * n), current_stream()))
+        check(load().thsp_memcpy_d2d(C.c_void_p(out.data_ptr() + 4 * n), color, C.c_size_t(4 * n), current_stream()))
+        torch.cuda.synchronize()
+        h = out.cpu().numpy()
+        return np.array(list(cp), dtype=np.int32), h[:n].copy(), h[n:].copy()
+
+    def sweep(self, r: "H.Vector", x: "H.Vector"):
+        A = self.A
+        check(load().thsp_symgs_f64(self.plan, A.nrow, ptr(A.row_ptr), ptr(A.col_ind), ptr(A.values), ptr(self.diagonal.values),
+                                    ptr(r.values), ptr(x.values), current_stream()))
+
+    def __del__(self):
+        try:
+            load().thsp_symgs_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+
+def pcg(A: "H.CSRMatrix", b: "H.Vector", x: "H.Vector", tol: float = 1e-10, maxit: int = 1000, precond: str = "none",
+        M: "SymGS | None" = None, diagonal: "H.Vector | None" = None):
+    """thsp_cg_f64: the whole loop inside the library (scalars on the device, canonical dots).  precond: none | jacobi |
+    symgs.  Returns (iterations, ||r|| / ||b||)."""
+    import torch
+    kind = {"none": 0, "jacobi": 1, "symgs": 2}[precond]
+    if kind == 2 and M is None:
+        M = SymGS(A, diagonal)
+    d = M.diagonal if M is not None else (diagonal if diagonal is not None else (csr_diagonal(A) if kind else None))
+    n = A.nrow
+    work = torch.empty(int(load().thsp_cg_work_doubles(n)), dtype=torch.float64, device=A.values.device)
+    it, rel = C.c_int(0), C.c_double(0.0)
+    check(load().thsp_cg_f64(A.plan(), n, kind, M.plan if M is not None else None, ptr(A.row_ptr), ptr(A.col_ind), ptr(A.values),
+                             ptr(d.values) if d is not None else None, ptr(b.values), ptr(x.values), maxit, C.c_double(tol), ptr(work),
+                             C.byref(it), C.byref(rel), current_stream()))
+    return it.value, rel.value
+
+
 def jacobi(A: "H.CSRMatrix", b: "H.Vector", x: "H.Vector", sweeps: int, omega: float = 1.0, diag: "H.Vector | None" = None):
     """`sweeps` damped Jacobi sweeps x += omega D^-1 (b - A x).  Returns ||b - A x|| / ||b|| after the last one."""
     n = A.nrow

@@ -66,6 +66,10 @@ THSP_API int thsp_memcpy_d2h(void* dst_host, const void* src, size_t bytes, thsp
 THSP_API int thsp_memcpy_d2d(void* dst, const void* src, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_memset(void* dst, int byte, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_prefetch(const void* managed_ptr, size_t bytes, int to_device, thsp_stream_t stream);
+/* cudaMemAdviseSetReadMostly on a managed array: a processor that reads it gets its own read-only copy instead of
+ * taking the pages away from the other one.  For matrix arrays, which main.cpp:46-52 walks on the host between two
+ * GPU uses: the copy in HBM stays valid and the next kernel does not wait for 84 MB to come back over PCIe. */
+THSP_API int thsp_advise_read_mostly(const void* managed_ptr, size_t bytes);
 THSP_API int thsp_stream_sync(thsp_stream_t stream);
 THSP_API int thsp_device_sync(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
@@ -233,15 +237,41 @@ THSP_API int thsp_check_vector_f64(int64_t nx, const double* x, int64_t ny, cons
                                    thsp_stream_t stream);
 
 /* ------------------------------------------------ callers above the path */
-/* The reference keeps a `diagonal` array "for SymGS" (include/matrix.h:36,81) and never uses it.  These two
- * are what a smoother needs from the library; CG and Jacobi themselves are compositions of CSRMatrixMatVector,
- * vec_dot and vec_axpby (arm-spmv_b200/solvers.py). */
-/* diag[i] = sum of the stored entries (i, i) of row i, 0 if none */
+/* The reference keeps a `diagonal` array "for SymGS" (include/matrix.h:36,81; src/matrix.cpp:146-153, 491-499) and the
+ * vector kernels of a Krylov loop (src/vec_vec.cpp:15-94, src/vector.cpp:96-159) without a caller.  csrc/solvers.cu. */
+/* diag[i] = sum of the stored entries (i, i) of row i, 0 if none.  Equals the reference's packed `diagonal` whenever that
+ * is usable at all: a row-sorted COO with one diagonal entry per row (the packing is by COO order, src/matrix.cpp:146-153). */
 THSP_API int thsp_csr_diagonal_f64(int nrow, const int* row_ptr, const int* col_ind, const double* val, double* diag,
                                    thsp_stream_t stream);
 /* x[i] += omega * r[i] / diag[i] */
 THSP_API int thsp_jacobi_update_f64(int64_t n, double omega, const double* diag, const double* r, double* x,
                                     thsp_stream_t stream);
+/* Symmetric Gauss-Seidel.  The plan colours the rows (deterministic greedy colouring, <= 64 colours, any sparsity
+ * pattern) and groups them by colour; thsp_symgs_f64 does one forward and one backward sweep
+ *     s = r_i - sum_j a_ij x_j ; s += x_i d_i ; x_i = s / d_i        (d = `diagonal`, one value per row)
+ * colour by colour, a thread per row in stored order, unfused arithmetic: the same bits as a serial walk over the same
+ * colours (the checker's twin in oracle/oracle.c).  thsp_symgs_plan_info: colour count, colouring rounds, colour offsets (host, ncolors + 1 ints) and the
+ * device arrays perm (rows grouped by colour) / color (colour of each row). */
+typedef struct thsp_symgs_plan thsp_symgs_plan;
+THSP_API int thsp_symgs_plan_create(thsp_symgs_plan** plan, int nrow, const int* row_ptr, const int* col_ind, thsp_stream_t stream);
+THSP_API int thsp_symgs_plan_destroy(thsp_symgs_plan* plan);
+THSP_API int thsp_symgs_plan_info(const thsp_symgs_plan* plan, int* ncolors, int* rounds, int* color_ptr_host, int capacity,
+                                  const int** perm_dev, const int** color_dev);
+THSP_API int thsp_symgs_f64(const thsp_symgs_plan* plan, int nrow, const int* row_ptr, const int* col_ind, const double* val,
+                            const double* diagonal, const double* r, double* x, thsp_stream_t stream);
+/* vec_dot (src/vec_vec.cpp:15-29) in the canonical order (32-element butterflies, index-bit tree: csrc/tree_sum.cuh),
+ * result on the device; tile_scratch = ceil(n/32) doubles. */
+THSP_API int thsp_dot_canonical_dev_f64(int64_t n, const double* x, const double* y, double* tile_scratch, double* out_dev,
+                                        thsp_stream_t stream);
+/* Preconditioned conjugate gradients for a symmetric positive definite CSR matrix: A = its plan (the SpMV), precond 0 none /
+ * 1 Jacobi (z = r / diagonal) / 2 one SymGS sweep from z = 0 (needs M and the matrix arrays).  Vector updates in the
+ * reference's forms (AddScaled, vec_axpby alpha == 1), dots in the canonical order, scalars on the device; the host reads
+ * ||r||^2 once per iteration.  work = thsp_cg_work_doubles(n) doubles of device memory.  Stops at ||r|| / ||b|| <= tol or
+ * maxit; *iters / *relres (host) report where.  Synchronous. */
+THSP_API int64_t thsp_cg_work_doubles(int64_t n);
+THSP_API int thsp_cg_f64(const thsp_csr_plan* A, int n, int precond, const thsp_symgs_plan* M, const int* row_ptr, const int* col_ind,
+                         const double* val, const double* diagonal, const double* b, double* x, int maxit, double tol, double* work,
+                         int* iters, double* relres, thsp_stream_t stream);
 
 /* --------------------------------------------- row-block partition (multi-GPU) ------ */
 /* *MatVectorNuma (src/mat_vec.cpp:230-268): equal row blocks, last takes the remainder. Host-only. */

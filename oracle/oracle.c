@@ -471,3 +471,109 @@ ORACLE_API uint64_t oracle_hash_f64(int64_t n, const double *v, uint64_t first)
     }
     return h;
 }
+
+/* ------------------------------------------------ SymGS and CG (no reference counterpart) -- */
+/* The reference prepares for both (`diagonal` "for SymGS", include/matrix.h:36,81; vec_dot / vec_axpby / AddScaled without
+ * a caller) and implements neither.  These restate what arm-spmv_b200/csrc/solvers.cu computes, serially, so that the
+ * tests can demand the same bits. */
+
+/* One row of a Gauss-Seidel sweep in the HPCG form: s = r_i - sum_j a_ij x_j over ALL stored entries of the row (the
+ * diagonal included), then s += x_i d_i and x_i = s / d_i. */
+static void symgs_row(int i, const int *rp, const int *ci, const double *va, const double *diag, const double *r, double *x)
+{
+    double s = r[i];
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+        double t = va[p] * x[ci[p]];
+        s = s - t;
+    }
+    double u = x[i] * diag[i];
+    s = s + u;
+    x[i] = s / diag[i];
+}
+
+/* Multicolour symmetric sweep: colours ascending then descending, rows of a colour in the order of perm (they do not
+ * touch each other, so any order gives the same bits).  color_ptr has ncolors + 1 entries. */
+ORACLE_API void oracle_symgs(int ncolors, const int *color_ptr, const int *perm, const int *rp, const int *ci, const double *va,
+                             const double *diag, const double *r, double *x)
+{
+    for (int c = 0; c < ncolors; ++c)
+        for (int k = color_ptr[c]; k < color_ptr[c + 1]; ++k) symgs_row(perm[k], rp, ci, va, diag, r, x);
+    for (int c = ncolors - 1; c >= 0; --c)
+        for (int k = color_ptr[c]; k < color_ptr[c + 1]; ++k) symgs_row(perm[k], rp, ci, va, diag, r, x);
+}
+
+/* The textbook sequential sweep (rows 0..n-1, then n-1..0): what the multicolour sweep is a reordering of. */
+ORACLE_API void oracle_symgs_sequential(int n, const int *rp, const int *ci, const double *va, const double *diag, const double *r,
+                                        double *x)
+{
+    for (int i = 0; i < n; ++i) symgs_row(i, rp, ci, va, diag, r, x);
+    for (int i = n - 1; i >= 0; --i) symgs_row(i, rp, ci, va, diag, r, x);
+}
+
+/* dot product in the canonical order: products per tile of 32 reduced by the xor-butterfly, tiles by the index-bit tree */
+static double dot_canonical(int64_t n, const double *a, const double *b)
+{
+    int64_t ntiles = (n + 31) / 32;
+    double *tile = (double *)malloc(sizeof(double) * (size_t)(ntiles > 0 ? ntiles : 1));
+    for (int64_t t = 0; t < ntiles; ++t) {
+        double v[32], w[32];
+        for (int l = 0; l < 32; ++l) {
+            int64_t i = t * 32 + l;
+            v[l] = i < n ? a[i] * b[i] : 0.0;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            for (int l = 0; l < 32; ++l) w[l] = v[l] + v[l ^ o];
+            for (int l = 0; l < 32; ++l) v[l] = w[l];
+        }
+        tile[t] = v[0];
+    }
+    double r = oracle_tree_sum(ntiles, tile);
+    free(tile);
+    return r;
+}
+ORACLE_API double oracle_dot_canonical(int64_t n, const double *a, const double *b) { return dot_canonical(n, a, b); }
+
+/* Preconditioned CG exactly as thsp_cg_f64 runs it: r = b - A x through CSRMatrixMatVector + vec_axpby(1, b, -1, .),
+ * x += alpha p and r += (-alpha) A p through AddScaled, p = beta p + z through vec_axpby(1, z, beta, p), dots canonical.
+ * precond 0 none, 1 Jacobi, 2 one multicolour SymGS sweep from z = 0.  Returns the iteration count; *relres = ||r||/||b||. */
+ORACLE_API int oracle_cg(int n, const int *rp, const int *ci, const double *va, const double *diag, int precond, int ncolors,
+                         const int *color_ptr, const int *perm, const double *b, double *x, int maxit, double tol, double *relres)
+{
+    double *r = (double *)calloc((size_t)n, sizeof(double)), *p = (double *)calloc((size_t)n, sizeof(double));
+    double *Ap = (double *)calloc((size_t)n, sizeof(double)), *zb = (double *)calloc((size_t)n, sizeof(double));
+    double *z = precond ? zb : r;
+    oracle_csr_spmv(n, rp, ci, va, x, r);                 /* r = 0 + A x */
+    oracle_axpby(n, 1.0, b, -1.0, r, r);                  /* r = -1*r + b */
+    double bb = dot_canonical(n, b, b), rr = dot_canonical(n, r, r);
+#define PRECONDITION()                                                                                      \
+    do {                                                                                                    \
+        if (precond == 1) for (int i = 0; i < n; ++i) z[i] = r[i] / diag[i];                                \
+        else if (precond == 2) { memset(z, 0, sizeof(double) * (size_t)n); oracle_symgs(ncolors, color_ptr, perm, rp, ci, va, diag, r, z); } \
+    } while (0)
+    PRECONDITION();
+    memcpy(p, z, sizeof(double) * (size_t)n);
+    double rz = precond ? dot_canonical(n, r, z) : rr;
+    double bnorm = bb > 0.0 ? sqrt(bb) : 1.0;
+    double rel = sqrt(rr) / bnorm;
+    int it = 0;
+    while (it < maxit && rel > tol) {
+        memset(Ap, 0, sizeof(double) * (size_t)n);
+        oracle_csr_spmv(n, rp, ci, va, p, Ap);
+        double pAp = dot_canonical(n, p, Ap);
+        double alpha = rz / pAp;
+        oracle_add_scaled(n, alpha, p, x);
+        oracle_add_scaled(n, -alpha, Ap, r);
+        rr = dot_canonical(n, r, r);
+        PRECONDITION();
+        double rz_new = precond ? dot_canonical(n, r, z) : rr;
+        double beta = rz_new / rz;
+        rz = rz_new;
+        oracle_axpby(n, 1.0, z, beta, p, p);
+        rel = sqrt(rr) / bnorm;
+        ++it;
+    }
+#undef PRECONDITION
+    if (relres) *relres = rel;
+    free(r); free(p); free(Ap); free(zb);
+    return it;
+}

@@ -238,6 +238,35 @@ class Oracle(_Base):
         v = _d(v)
         return int(self.fn("hash_f64", C.c_uint64)(C.c_int64(len(v)), _vp(v), C.c_uint64(first)))
 
+    def symgs(self, color_ptr, perm, rp, ci, va, diag, r, x):
+        x = _d(x).copy()
+        cp, perm, rp, ci = _i(color_ptr), _i(perm), _i(rp), _i(ci)
+        va, diag, r = _d(va), _d(diag), _d(r)
+        self.fn("symgs")(C.c_int(len(cp) - 1), _vp(cp), _vp(perm), _vp(rp), _vp(ci), _vp(va), _vp(diag), _vp(r), _vp(x))
+        return x
+
+    def symgs_sequential(self, rp, ci, va, diag, r, x):
+        x = _d(x).copy()
+        rp, ci, va, diag, r = _i(rp), _i(ci), _d(va), _d(diag), _d(r)
+        self.fn("symgs_sequential")(C.c_int(len(rp) - 1), _vp(rp), _vp(ci), _vp(va), _vp(diag), _vp(r), _vp(x))
+        return x
+
+    def dot_canonical(self, a, b):
+        a, b = _d(a), _d(b)
+        return float(self.fn("dot_canonical", C.c_double)(C.c_int64(len(a)), _vp(a), _vp(b)))
+
+    def cg(self, rp, ci, va, diag, b, x0, maxit, tol, precond=0, color_ptr=None, perm=None):
+        rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+        x = _d(x0).copy()
+        diag = None if diag is None else _d(diag)
+        cp = None if color_ptr is None else _i(color_ptr)
+        pm = None if perm is None else _i(perm)
+        rel = C.c_double(0.0)
+        it = self.fn("cg", C.c_int)(C.c_int(len(rp) - 1), _vp(rp), _vp(ci), _vp(va), _vp(diag), C.c_int(precond),
+                                    C.c_int(0 if cp is None else len(cp) - 1), _vp(cp), _vp(pm), _vp(b), _vp(x), C.c_int(maxit),
+                                    C.c_double(tol), C.byref(rel))
+        return x, int(it), rel.value
+
     def partition(self, n, nparts, part):
         s, c = C.c_int(), C.c_int()
         self.fn("partition")(C.c_int(n), C.c_int(nparts), C.c_int(part), C.byref(s), C.byref(c))

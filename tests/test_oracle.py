@@ -162,3 +162,32 @@ def test_partition_and_slice(oracle):
             sub, nnz = oracle.csr_slice(rp, s, c)
             assert sub[0] == 0 and sub[-1] == nnz == rp[s + c] - rp[s]
         assert covered == n
+
+
+def test_symgs_and_cg_restatements(oracle):
+    """The solver twins of oracle.c (no reference counterpart: the reference keeps `diagonal` "for SymGS" and never sweeps):
+    the multicolour sweep with one row per colour IS the sequential sweep; preconditioned CG solves the stencil system and
+    the SymGS preconditioner saves iterations; the canonical dot is a dot."""
+    n = 7
+    N = n ** 3
+    rp, ci, va = oracle.gen_stencil27_csr(n)
+    diag = np.full(N, 26.0)
+    b = oracle.gen_vector(N, 3)
+    cp, perm = np.arange(N + 1, dtype=np.int32), np.arange(N, dtype=np.int32)
+    x0 = oracle.gen_vector(N, 4)
+    assert oracle.symgs(cp, perm, rp, ci, va, diag, b, x0).tobytes() == oracle.symgs_sequential(rp, ci, va, diag, b, x0).tobytes()
+    M = np.zeros((N, N))
+    for r in range(N):
+        M[r, ci[rp[r]:rp[r + 1]]] = va[rp[r]:rp[r + 1]]
+    want = np.linalg.solve(M, b)
+    its = {}
+    for kind in (0, 1, 2):
+        x, it, rel = oracle.cg(rp, ci, va, diag, b, np.zeros(N), 300, 1e-12, kind, cp, perm)
+        assert rel <= 1e-12 and np.max(np.abs(x - want)) <= 1e-10 * np.max(np.abs(want))
+        its[kind] = it
+    assert its[2] < its[0]
+    a, c = oracle.gen_vector(1000, 1) - 0.5, oracle.gen_vector(1000, 2)
+    assert abs(oracle.dot_canonical(a, c) - float(np.dot(a, c))) <= 1e-13 * float(np.sum(np.abs(a * c)))
+    y = oracle.gen_vector(777, 9)
+    assert oracle.tree_sum(oracle.tile_sumsq(y)) == oracle.dot_canonical(y, y)
+    assert (oracle.hash_f64(y[:300], 10) + oracle.hash_f64(y[300:], 310)) % (1 << 64) == oracle.hash_f64(y, 10)
