@@ -114,11 +114,21 @@ __host__ __device__ inline size_t stream_warp_bytes(int stages, int chunk)
     return (b + 127) & ~(size_t)127;
 }
 
+// Epilogue of a Gauss-Seidel colour (solvers.cu): the tile's rows are rows `rows[.]` of the matrix the caller permuted by
+// colour; instead of y_row = sum the kernel does  s = r_i - sum ; s += x_i d_i ; x_i = s / d_i  for i = rows[row].
 template <typename V>
+struct GsEpilogue {
+    const int* rows = nullptr;
+    const V* r = nullptr;
+    const V* diag = nullptr;
+    V* x = nullptr;   // the same vector the kernel gathers from: rows of one colour never read each other's entries
+};
+
+template <typename V, bool kGs>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
-                      V* __restrict__ tile_ss, int* __restrict__ stale)
+                      V* __restrict__ tile_ss, int* __restrict__ stale, GsEpilogue<V> gs)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -166,6 +176,8 @@ __global__ void __launch_bounds__(768, 1)
     unsigned c_parity = 0;
     int rs = 0, re = 0;
     V sum = V(0), yold = V(0);
+    int gs_i = 0;
+    V gs_r = V(0), gs_d = V(1);
     int lead = S - 1;  // produce-only iterations that fill the ring
 
     // One loop, one produce site, one consume site (keeps the code - and the registers - small).
@@ -232,6 +244,11 @@ __global__ void __launch_bounds__(768, 1)
             c_nch = max(1, (c_te - c_al + CH - 1) / CH);
             sum = V(0);
             yold = (accumulate && row < nrow) ? y[row] : V(0);
+            if (kGs && row < nrow) {   // fetched now, used when the tile is done: the loads are off the critical path
+                gs_i = gs.rows[row];
+                gs_r = gs.r[gs_i];
+                gs_d = gs.diag[gs_i];
+            }
         }
         mbar_wait(bar + c_stage, c_parity);
         __syncwarp();
@@ -262,7 +279,15 @@ __global__ void __launch_bounds__(768, 1)
         if (c_stage == 0) c_parity ^= 1u;
         if (++c_chunk == c_nch) {
             const V ynew = accumulate ? add_rn(yold, sum) : sum;
-            if (row < nrow) y[row] = ynew;
+            if (kGs) {
+                if (row < nrow) {
+                    V sv = add_rn(gs_r, -sum);
+                    sv = add_rn(sv, mul_rn(gs.x[gs_i], gs_d));   // own entry read through the pointer it is written through
+                    gs.x[gs_i] = div_rn(sv, gs_d);
+                }
+            } else if (row < nrow) {
+                y[row] = ynew;
+            }
             if (tile_ss) {   // the tile's partial of sum y_i^2, in the canonical order of tree_sum.cuh: nobody reads y again
                 V q = row < nrow ? mul_rn(ynew, ynew) : V(0);
 #pragma unroll
@@ -278,7 +303,8 @@ __global__ void __launch_bounds__(768, 1)
 
 template <typename V>
 static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
-                      const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, int* stale = nullptr)
+                      const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, int* stale = nullptr,
+                      GsEpilogue<V> gs = GsEpilogue<V>())
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
@@ -291,13 +317,15 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     THSP_CUDA(cudaGetDevice(&dev));
     size_t& cur = configured[dev & 15][sizeof(V) == 8 ? 0 : 1];
     if (smem > cur) {
-        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cur = 227 * 1024;
     }
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    csr_stream_kernel<V><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale);
+    if (gs.rows) csr_stream_kernel<V, true><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs);
+    else csr_stream_kernel<V, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -700,6 +728,16 @@ static int* stale_slot_acquire()
 }
 
 namespace thsp {
+// One colour of a Gauss-Seidel sweep through the stream kernel (solvers.cu): rows [0, nrow) of a CSR whose row pointers
+// index into col / val holding nnz_total entries, `rows` = their numbers in the unpermuted matrix.
+int stream_gs_color(int nrow, int nnz_total, double mean_len, const int* rp, const int* col, const double* val, const int* rows,
+                    const double* r, const double* diag, double* x, cudaStream_t s)
+{
+    StreamCfg cfg = default_stream_cfg<double>(1 << 20, (int)(mean_len * (1 << 20)));
+    GsEpilogue<double> gs;
+    gs.rows = rows; gs.r = r; gs.diag = diag; gs.x = x;
+    return run_stream<double>(cfg, sm_count(), nrow, nnz_total, rp, col, val, x, nullptr, 0, s, nullptr, nullptr, gs);
+}
 void warm_stale_page() { stale_slot_acquire(); }   // thsp_prepare_conversions: the page exists before the first plan is timed
 }
 

@@ -31,14 +31,13 @@ inline T* alloc(size_t n)
     return static_cast<T*>(alloc_managed_bytes((n ? n : 1) * sizeof(T)));
 }
 
-// Matrix arrays: written once (by a conversion kernel, the GPU parser or the scanf loop), then only read - by kernels and,
-// in main.cpp:46-52, by a host loop in between.  Read-mostly advice lets both processors keep a copy.
+// Matrix arrays.  (Tried: cudaMemAdviseSetReadMostly, so that the host loop of main.cpp:46-52 would leave the copy in HBM
+// valid.  Measured on B200 / driver 580: kernels WRITING such arrays - every conversion, the GPU parser - crawl, COO->CSC of
+// 5.2 M entries 4.8 -> 883 ms, the whole driver run 2.3 -> 4.6 s.  Plain managed memory it is.)
 template <class T>
 inline T* alloc_matrix(size_t n)
 {
-    T* p = alloc<T>(n);
-    ok(thsp_advise_read_mostly(p, (n ? n : 1) * sizeof(T)), "read-mostly advice");
-    return p;
+    return alloc<T>(n);
 }
 
 // 0 plain host, 1 device, 2 managed, 3 pinned host, -1 the CUDA runtime could not say.  Library-owned arrays are

@@ -5,7 +5,7 @@
 // src/vec_vec.cpp:15-94; Vector::AddScaled / Add2Scaled, src/vector.cpp:96-159) without a caller.  Here:
 //
 //  SymGS  one symmetric Gauss-Seidel sweep x <- SGS(A, r; x) that consumes the diagonal array: per row
-//             s = r_i - sum_j a_ij x_j ;  s += x_i d_i ;  x_i = s / d_i          (all j of the row, the diagonal included)
+//             t = sum_j a_ij x_j (from 0, stored order, the diagonal included) ;  s = r_i - t ;  s += x_i d_i ;  x_i = s / d_i
 //         forward over the rows, then backward.  Rows are grouped by COLOUR (no two rows of a colour touch each other), a
 //         colour is one kernel launch with a thread per row adding its row left to right with unfused arithmetic; colours
 //         ascending, then descending.  Inside a colour the rows are independent, so the result does not depend on the
@@ -30,6 +30,8 @@
 namespace thsp {
 
 int exclusive_scan(int n, const int* in, int* out, cudaStream_t s);   // convert.cu
+int stream_gs_color(int nrow, int nnz_total, double mean_len, const int* rp, const int* col, const double* val, const int* rows,
+                    const double* r, const double* diag, double* x, cudaStream_t s);   // csr_spmv.cu
 
 __host__ __device__ inline uint64_t color_prio(uint64_t v)
 {
@@ -42,7 +44,8 @@ __host__ __device__ inline uint64_t color_prio(uint64_t v)
 // ---- colouring ---------------------------------------------------------------------------------------------------
 // assign: every uncoloured row takes the smallest colour none of its already coloured out-neighbours has
 __global__ void __launch_bounds__(256) color_assign_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
-                                                           const int* __restrict__ cin, int* __restrict__ cout, int* __restrict__ overflow)
+                                                           const int* __restrict__ cin, int* __restrict__ cout, int* __restrict__ overflow,
+                                                           const unsigned long long* __restrict__ forbid)
 {
     const int v = blockIdx.x * 256 + threadIdx.x;
     if (v >= nrow) return;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(256) color_assign_kernel(int nrow, const int* 
         cout[v] = c;
         return;
     }
-    unsigned long long used = 0ull;
+    unsigned long long used = forbid[v];   // colours of rows that point at v without v pointing back (learnt from lost conflicts)
     for (int p = rp[v]; p < rp[v + 1]; ++p) {
         const int u = ci[p];
         if (u == v || u < 0 || u >= nrow) continue;
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(256) color_assign_kernel(int nrow, const int* 
 // resolve: an edge v -> u whose ends got the same colour sends one of them back: the one coloured in this round
 // (if only one was), else the one with the lower hash.  All writers write the same value: no race that matters.
 __global__ void __launch_bounds__(256) color_resolve_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
-                                                            const int* __restrict__ cin, const int* __restrict__ cout, int* __restrict__ redo)
+                                                            const int* __restrict__ cin, const int* __restrict__ cout, int* __restrict__ redo,
+                                                            unsigned long long* __restrict__ forbid)
 {
     const int v = blockIdx.x * 256 + threadIdx.x;
     if (v >= nrow) return;
@@ -89,7 +93,11 @@ __global__ void __launch_bounds__(256) color_resolve_kernel(int nrow, const int*
             const uint64_t pu = color_prio((uint64_t)u);
             u_loses = pu < pv || (pu == pv && u < v);
         }
-        redo[u_loses ? u : v] = 1;
+        const int loser = u_loses ? u : v;
+        redo[loser] = 1;
+        // The loser may not see the winner (an entry (v, u) without (u, v)): without this it would pick the same colour
+        // again next round, for ever.  A set union: the order of the atomics does not matter.
+        atomicOr(forbid + loser, 1ull << cv);
     }
 }
 __global__ void __launch_bounds__(256) color_apply_kernel(int nrow, const int* __restrict__ cout, int* __restrict__ redo,
@@ -121,6 +129,38 @@ __global__ void __launch_bounds__(256) color_place_kernel(int nrow, const int* _
     if (v < nrow && color[v] == c) perm[base + pos[v]] = v;
 }
 
+// ---- the matrix permuted by colour (rows of a colour contiguous, columns unchanged): what lets a colour be STREAMED ----
+__global__ void __launch_bounds__(256) perm_len_kernel(int nrow, const int* __restrict__ perm, const int* __restrict__ rp,
+                                                       int* __restrict__ len, int* __restrict__ maxlen)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    int l = 0;
+    if (k < nrow) {
+        const int i = perm[k];
+        l = rp[i + 1] - rp[i];
+        len[k] = l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
+    if ((threadIdx.x & 31) == 0 && l > 0) atomicMax(maxlen, l);
+}
+// a warp per permuted row copies the row's entries (coalesced on both sides)
+__global__ void __launch_bounds__(256) perm_copy_kernel(int nrow, const int* __restrict__ perm, const int* __restrict__ rp,
+                                                        const int* __restrict__ ci, const double* __restrict__ va,
+                                                        const int* __restrict__ prp, int* __restrict__ pci, double* __restrict__ pva)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, GW = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t k = gw; k < nrow; k += GW) {
+        const int i = perm[k];
+        const int src = rp[i], n = rp[i + 1] - src, dst = prp[k];
+        for (int e = lane; e < n; e += 32) {
+            pci[dst + e] = ld_stream(ci + src + e);
+            pva[dst + e] = ld_stream(va + src + e);
+        }
+    }
+}
+
 // ---- one colour of a sweep: a thread per row, the row's entries left to right ---------------------------------------
 __global__ void __launch_bounds__(256) symgs_color_kernel(int count, const int* __restrict__ rows, const int* __restrict__ rp,
                                                           const int* __restrict__ ci, const double* __restrict__ va,
@@ -129,10 +169,11 @@ __global__ void __launch_bounds__(256) symgs_color_kernel(int count, const int* 
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= count) return;
     const int i = rows[k];
-    double s = r[i];
+    double t = 0.0;
     const int e1 = __ldg(rp + i + 1);
-    for (int p = __ldg(rp + i); p < e1; ++p) s = add_rn(s, -mul_rn(__ldg(va + p), x[__ldg(ci + p)]));   // x of other colours only changes between launches
+    for (int p = __ldg(rp + i); p < e1; ++p) t = add_rn(t, mul_rn(__ldg(va + p), x[__ldg(ci + p)]));   // x of other colours only changes between launches
     const double d = diag[i];
+    double s = add_rn(r[i], -t);
     s = add_rn(s, mul_rn(x[i], d));
     x[i] = __ddiv_rn(s, d);
 }
@@ -201,11 +242,54 @@ struct thsp_symgs_plan {
     int* perm = nullptr;            // device: rows grouped by colour, ascending inside a colour
     int* color = nullptr;           // device: colour of every row
     std::vector<int> color_ptr;     // host: [ncolors + 1]
+    // The matrix permuted by colour (a snapshot taken when the plan is made: rows of a colour are one contiguous CSR
+    // slab, which the TMA stream kernel of csr_spmv.cu sweeps with its Gauss-Seidel epilogue).  nullptr = a thread per
+    // row on the caller's arrays.
+    int nnz = 0;
+    double mean_len = 0.0;
+    int *prp = nullptr, *pci = nullptr;
+    double* pva = nullptr;
 };
 
 extern "C" {
 
-int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, const int* col_ind, thsp_stream_t stream)
+static int symgs_permute(thsp_symgs_plan* p, const int* row_ptr, const int* col_ind, const double* val, cudaStream_t s)
+{
+    const int nrow = p->nrow;
+    int nnz = 0;
+    THSP_CUDA(cudaMemcpyAsync(&nnz, row_ptr + nrow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    if (nnz <= 0) return 0;
+    int *len = nullptr, *mx = nullptr;
+    THSP_CUDA(cudaMalloc(&len, sizeof(int) * ((size_t)nrow + 2)));
+    mx = len + nrow + 1;
+    THSP_CUDA(cudaMemsetAsync(mx, 0, sizeof(int), s));
+    perm_len_kernel<<<div_up(nrow, 256), 256, 0, s>>>(nrow, p->perm, row_ptr, len, mx);
+    THSP_LAUNCH_CHECK();
+    int maxlen = 0;
+    THSP_CUDA(cudaMemcpyAsync(&maxlen, mx, sizeof(int), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    const double mean = (double)nnz / nrow;
+    if (mean < 4.0 || maxlen > 2048 || nrow < 4096) {   // the stream kernel's own conditions (thsp_csr_plan_create)
+        cudaFree(len);
+        return 0;
+    }
+    THSP_CUDA(cudaMalloc(&p->prp, sizeof(int) * ((size_t)nrow + 1)));
+    THSP_CUDA(cudaMalloc(&p->pci, sizeof(int) * (size_t)nnz));
+    THSP_CUDA(cudaMalloc(&p->pva, sizeof(double) * (size_t)nnz));
+    if (exclusive_scan(nrow, len, p->prp, s)) return 1;
+    perm_copy_kernel<<<std::min(div_up((int64_t)nrow * 32, 256), sm_count() * 16), 256, 0, s>>>(nrow, p->perm, row_ptr, col_ind, val, p->prp,
+                                                                                             p->pci, p->pva);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaStreamSynchronize(s));
+    cudaFree(len);
+    p->nnz = nnz;
+    p->mean_len = mean;
+    return 0;
+}
+
+int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, const int* col_ind, const double* val,
+                           thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
     THSP_REQUIRE(out != nullptr && nrow >= 0, "bad arguments");
@@ -216,6 +300,9 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
     *out = p;
     if (nrow == 0) return 0;
     int *cin = nullptr, *cout = nullptr, *redo = nullptr, *small = nullptr;
+    unsigned long long* forbid = nullptr;
+    THSP_CUDA(cudaMalloc(&forbid, sizeof(unsigned long long) * (size_t)nrow));
+    THSP_CUDA(cudaMemsetAsync(forbid, 0, sizeof(unsigned long long) * (size_t)nrow, s));
     THSP_CUDA(cudaMalloc(&cin, sizeof(int) * (size_t)nrow));
     THSP_CUDA(cudaMalloc(&cout, sizeof(int) * ((size_t)nrow + 1)));
     THSP_CUDA(cudaMalloc(&redo, sizeof(int) * ((size_t)nrow + 1)));
@@ -226,9 +313,9 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
     int rc = 0;
     for (int round = 0; round < 200; ++round) {
         THSP_CUDA(cudaMemsetAsync(small, 0, sizeof(int) * 4, s));
-        color_assign_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, cout, small + 1);
+        color_assign_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, cout, small + 1, forbid);
         THSP_LAUNCH_CHECK();
-        color_resolve_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, cout, redo);
+        color_resolve_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, cout, redo, forbid);
         THSP_LAUNCH_CHECK();
         color_apply_kernel<<<grid, 256, 0, s>>>(nrow, cout, redo, cin, small);
         THSP_LAUNCH_CHECK();
@@ -273,14 +360,15 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
         }
         p->color = cin;
         cin = nullptr;
+        if (val && symgs_permute(p, row_ptr, col_ind, val, s)) rc = 1;
     }
     if (cin) cudaFree(cin);
+    cudaFree(forbid);
     cudaFree(cout);
     cudaFree(redo);
     cudaFree(small);
     if (rc) {
-        if (p->perm) cudaFree(p->perm);
-        delete p;
+        thsp_symgs_plan_destroy(p);
         *out = nullptr;
     }
     return rc;
@@ -291,7 +379,17 @@ int thsp_symgs_plan_destroy(thsp_symgs_plan* p)
     if (!p) return 0;
     if (p->perm) cudaFree(p->perm);
     if (p->color) cudaFree(p->color);
+    if (p->prp) cudaFree(p->prp);
+    if (p->pci) cudaFree(p->pci);
+    if (p->pva) cudaFree(p->pva);
     delete p;
+    return 0;
+}
+
+int thsp_symgs_plan_streams(const thsp_symgs_plan* p, int* streams)
+{
+    THSP_REQUIRE(p != nullptr && streams != nullptr, "null plan");
+    *streams = p->pva ? 1 : 0;
     return 0;
 }
 
@@ -316,6 +414,10 @@ static int symgs_sweep(const thsp_symgs_plan* p, const int* rp, const int* ci, c
             const int c = pass == 0 ? k : p->ncolors - 1 - k;
             const int off = p->color_ptr[c], cnt = p->color_ptr[c + 1] - off;
             if (cnt <= 0) continue;
+            if (p->pva && cnt >= 2048) {   // the colour's rows are a contiguous slab of the permuted copy: stream it
+                if (stream_gs_color(cnt, p->nnz, p->mean_len, p->prp + off, p->pci, p->pva, p->perm + off, r, diag, x, s)) return 1;
+                continue;
+            }
             symgs_color_kernel<<<div_up(cnt, 256), 256, 0, s>>>(cnt, p->perm + off, rp, ci, va, diag, r, x);
             THSP_LAUNCH_CHECK();
         }

@@ -54,12 +54,17 @@ class SymGS:
     """Symmetric Gauss-Seidel on the GPU (thsp_symgs_*): the smoother the reference's `diagonal` arrays were kept for
     (include/matrix.h:36,81).  The plan colours the rows once; sweep() does forward + backward, colour by colour."""
 
-    def __init__(self, A: "H.CSRMatrix", diagonal: "H.Vector | None" = None):
+    def __init__(self, A: "H.CSRMatrix", diagonal: "H.Vector | None" = None, snapshot: bool = True):
+        """snapshot: keep a copy of the matrix permuted by colour, so that colours are streamed (thsp_symgs_plan_create)."""
         self.A = A
         self.diagonal = diagonal if diagonal is not None else csr_diagonal(A)
         h = C.c_void_p()
-        check(load().thsp_symgs_plan_create(C.byref(h), A.nrow, ptr(A.row_ptr), ptr(A.col_ind), current_stream()))
+        check(load().thsp_symgs_plan_create(C.byref(h), A.nrow, ptr(A.row_ptr), ptr(A.col_ind), ptr(A.values) if snapshot else None,
+                                            current_stream()))
         self.plan = h
+        st = C.c_int(0)
+        check(load().thsp_symgs_plan_streams(h, C.byref(st)))
+        self.streams = bool(st.value)
         nc, rounds = C.c_int(), C.c_int()
         check(load().thsp_symgs_plan_info(h, C.byref(nc), C.byref(rounds), None, 0, None, None))
         self.ncolors, self.rounds = nc.value, rounds.value

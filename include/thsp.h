@@ -66,10 +66,6 @@ THSP_API int thsp_memcpy_d2h(void* dst_host, const void* src, size_t bytes, thsp
 THSP_API int thsp_memcpy_d2d(void* dst, const void* src, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_memset(void* dst, int byte, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_prefetch(const void* managed_ptr, size_t bytes, int to_device, thsp_stream_t stream);
-/* cudaMemAdviseSetReadMostly on a managed array: a processor that reads it gets its own read-only copy instead of
- * taking the pages away from the other one.  For matrix arrays, which main.cpp:46-52 walks on the host between two
- * GPU uses: the copy in HBM stays valid and the next kernel does not wait for 84 MB to come back over PCIe. */
-THSP_API int thsp_advise_read_mostly(const void* managed_ptr, size_t bytes);
 THSP_API int thsp_stream_sync(thsp_stream_t stream);
 THSP_API int thsp_device_sync(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
@@ -248,12 +244,18 @@ THSP_API int thsp_jacobi_update_f64(int64_t n, double omega, const double* diag,
                                     thsp_stream_t stream);
 /* Symmetric Gauss-Seidel.  The plan colours the rows (deterministic greedy colouring, <= 64 colours, any sparsity
  * pattern) and groups them by colour; thsp_symgs_f64 does one forward and one backward sweep
- *     s = r_i - sum_j a_ij x_j ; s += x_i d_i ; x_i = s / d_i        (d = `diagonal`, one value per row)
+ *     t = sum_j a_ij x_j (from 0, stored order) ; s = r_i - t ; s += x_i d_i ; x_i = s / d_i     (d = `diagonal`, one value per row)
  * colour by colour, a thread per row in stored order, unfused arithmetic: the same bits as a serial walk over the same
  * colours (the checker's twin in oracle/oracle.c).  thsp_symgs_plan_info: colour count, colouring rounds, colour offsets (host, ncolors + 1 ints) and the
  * device arrays perm (rows grouped by colour) / color (colour of each row). */
 typedef struct thsp_symgs_plan thsp_symgs_plan;
-THSP_API int thsp_symgs_plan_create(thsp_symgs_plan** plan, int nrow, const int* row_ptr, const int* col_ind, thsp_stream_t stream);
+/* val != NULL: the plan also keeps a copy of the matrix permuted by colour (a snapshot: make a new plan after changing the
+ * matrix), which lets each colour be swept by the TMA stream kernel of the CSR path instead of a thread per row - same
+ * arithmetic, same bits, several times the bandwidth on matrices the stream kernel takes (mean row length >= 4, longest
+ * row <= 2048).  *streams of thsp_symgs_plan_streams tells whether that copy exists. */
+THSP_API int thsp_symgs_plan_create(thsp_symgs_plan** plan, int nrow, const int* row_ptr, const int* col_ind, const double* val,
+                                    thsp_stream_t stream);
+THSP_API int thsp_symgs_plan_streams(const thsp_symgs_plan* plan, int* streams);
 THSP_API int thsp_symgs_plan_destroy(thsp_symgs_plan* plan);
 THSP_API int thsp_symgs_plan_info(const thsp_symgs_plan* plan, int* ncolors, int* rounds, int* color_ptr_host, int capacity,
                                   const int** perm_dev, const int** color_dev);

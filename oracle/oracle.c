@@ -477,15 +477,17 @@ ORACLE_API uint64_t oracle_hash_f64(int64_t n, const double *v, uint64_t first)
  * a caller) and implements neither.  These restate what arm-spmv_b200/csrc/solvers.cu computes, serially, so that the
  * tests can demand the same bits. */
 
-/* One row of a Gauss-Seidel sweep in the HPCG form: s = r_i - sum_j a_ij x_j over ALL stored entries of the row (the
- * diagonal included), then s += x_i d_i and x_i = s / d_i. */
+/* One row of a Gauss-Seidel sweep: t = sum_j a_ij x_j over ALL stored entries of the row (from 0.0, in stored order, the
+ * diagonal included - the row sum of CSRMatrixMatVector, src/mat_vec.cpp:58-62), s = r_i - t, then s += x_i d_i and
+ * x_i = s / d_i. */
 static void symgs_row(int i, const int *rp, const int *ci, const double *va, const double *diag, const double *r, double *x)
 {
-    double s = r[i];
+    double acc = 0.0;
     for (int p = rp[i]; p < rp[i + 1]; ++p) {
         double t = va[p] * x[ci[p]];
-        s = s - t;
+        acc = acc + t;
     }
+    double s = r[i] - acc;
     double u = x[i] * diag[i];
     s = s + u;
     x[i] = s / diag[i];

@@ -57,13 +57,13 @@ def _colouring_is_valid(rp, ci, color):
     return not np.any(color[rows[off]] == color[ci[off]])
 
 
-@pytest.mark.parametrize("which", ["stencil", "lap5", "nonsymmetric"])
+@pytest.mark.parametrize("which", ["stencil", "stencil40", "lap5", "nonsymmetric"])
 def test_symgs_matches_the_oracle_bit_for_bit(thsp, cuda, oracle, which):
     """thsp_symgs_f64 against oracle_symgs walking the same colours serially: same bits (rows of a colour do not touch each
     other, every row is added in stored order with unfused arithmetic).  The colouring itself is checked on the CPU."""
     from arm_spmv_b200 import host as H, solvers
-    if which == "stencil":
-        n = 14; N = n ** 3
+    if which in ("stencil", "stencil40"):
+        n = 14 if which == "stencil" else 40; N = n ** 3
         rp, ci, va = oracle.gen_stencil27_csr(n)
     elif which == "lap5":
         ri, cj, v = oracle.gen_lap5_coo(37); N = 37 * 37
@@ -82,8 +82,10 @@ def test_symgs_matches_the_oracle_bit_for_bit(thsp, cuda, oracle, which):
     assert _colouring_is_valid(rp, ci, color)
     for c in range(S.ncolors):
         assert np.all(color[perm[cp[c]:cp[c + 1]]] == c)
-    if which == "stencil":
+    if which in ("stencil", "stencil40"):
         assert S.ncolors >= 8        # a 27-point stencil needs 8
+    # 64000 rows: the plan keeps the matrix permuted by colour and the colours go through the TMA stream kernel
+    assert S.streams == (which == "stencil40")
     diag = host(S.diagonal.values)
     r = oracle.gen_vector(N, 5) - 0.5
     x0 = oracle.gen_vector(N, 6)
@@ -127,6 +129,18 @@ def test_cg_in_the_library_matches_the_oracle_iterates(thsp, cuda, oracle, preco
     if precond == "symgs":
         it0, _ = solvers.pcg(A, H.Vector(b), H.Vector(np.zeros(N)), tol=1e-11, maxit=500)
         assert it < it0
+        # the streamed sweep inside the loop: 40^3, five iterations, same bits as the serial twin
+        n2 = 40; N2 = n2 ** 3
+        rp2, ci2, va2 = oracle.gen_stencil27_csr(n2)
+        A2 = H.CSRMatrix(nrow=N2, ncol=N2, row_ptr=dev(rp2), col_ind=dev(ci2), values=dev(va2))
+        M2 = solvers.SymGS(A2)
+        assert M2.streams
+        cp2, perm2, _ = M2.coloring()
+        b2 = oracle.gen_vector(N2, 8)
+        x2 = H.Vector(np.zeros(N2))
+        solvers.pcg(A2, H.Vector(b2), x2, tol=0.0, maxit=5, precond="symgs", M=M2)
+        want2, _, _ = oracle.cg(rp2, ci2, va2, host(M2.diagonal.values), b2, np.zeros(N2), 5, 0.0, 2, cp2, perm2)
+        assert host(x2.values).tobytes() == want2.tobytes()
 
 
 def test_dot_canonical(thsp, cuda, oracle):
