@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     const V carry_in = __shfl_up_sync(full, tail, 1);   // inclusive scan of lane-1 = what flows into this lane
     const bool first_shared = __ldg(row_ptr + i0) < j0;
     if (lane == 0) carry_row[2 * run] = -1;
+    if (run == 0 && lane == 0) {   // the fix-up's list of long chains starts empty (it runs after this kernel)
+        carry_row[2 * nruns] = 0;
+        carry_row[2 * nruns + 1] = 0;
+    }
     __syncwarp();
     if (has_mark && (lane > 0 || head_any)) {
         V tot = head;
@@ -546,13 +550,19 @@ __global__ void __launch_bounds__(kMergeWarps * 32, 8)
     }
 }
 
+static constexpr int kFixShort = 64;     // slots one thread adds up itself; longer chains go to a whole CTA
+static constexpr int kFixMaxLong = 8192; // room in the list of long chains (more than that: the CTAs loop)
+
 template <typename V>
 __global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry_row, const V* __restrict__ carry_val,
-                                       V* __restrict__ y, const int* __restrict__ row_ptr, int nrow, int nnz, const int* __restrict__ stale)
+                                       V* __restrict__ y, const int* __restrict__ row_ptr, int nrow, int nnz, const int* __restrict__ stale,
+                                       int* __restrict__ long_count, int* __restrict__ long_first)
 {
     if (stale && __ldg(row_ptr + nrow) != nnz) return;   // the main kernel did not run: the carries are not there
     // Slots are in entry order, so partials of one row are consecutive (ignoring -1 holes).
-    // One thread per slot; the thread owning the FIRST slot of a row adds the whole chain in order.
+    // One thread per slot; the thread owning the FIRST slot of a row adds the chain in order - up to kFixShort slots.
+    // A hub row of a power-law matrix crosses ~1500 runs: one thread walking that chain took 0.2 ms of the R-MAT SpMV's
+    // 1.8 (a round trip per eight partials); such chains are listed and added up by a whole CTA each (the kernel below).
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int r = carry_row[i];
@@ -560,11 +570,17 @@ __global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry
     int k = i - 1;
     while (k >= 0 && carry_row[k] < 0) --k;
     if (k >= 0 && carry_row[k] == r) return;  // not the first slot of this row
-    // A hub row of a power-law matrix crosses hundreds of runs: fetch eight slots at a time so that the chain
-    // costs one memory round trip per eight partials instead of one each; the additions stay left to right.
     V acc = y[r];
-    bool open = true;
+    bool open = true, offered = false;
     for (int j0 = i; open && j0 < nslots; j0 += 8) {
+        if (j0 - i >= kFixShort && !offered) {   // still the same row: hand the whole chain over, y untouched
+            offered = true;
+            const int q = atomicAdd(long_count, 1);
+            if (q < kFixMaxLong) {
+                long_first[q] = i;
+                return;
+            }   // list full: this thread walks the chain itself after all
+        }
         int rj[8];
         V vj[8];
 #pragma unroll
@@ -581,6 +597,55 @@ __global__ void csr_merge_fixup_kernel(int nslots, const int* __restrict__ carry
         }
     }
     y[r] = acc;
+}
+
+// One CTA per long chain: find its end (first later slot of another row), every thread adds a contiguous piece in slot
+// order, the pieces are combined in thread order by a tree: deterministic, y[r] += total.
+template <typename V>
+__global__ void __launch_bounds__(256) csr_merge_fixup_long_kernel(int nslots, const int* __restrict__ carry_row,
+                                                                   const V* __restrict__ carry_val, V* __restrict__ y,
+                                                                   const int* __restrict__ long_count, const int* __restrict__ long_first,
+                                                                   const int* __restrict__ row_ptr, int nrow, int nnz,
+                                                                   const int* __restrict__ stale)
+{
+    __shared__ int s_end;
+    __shared__ V s_part[8];
+    if (stale && __ldg(row_ptr + nrow) != nnz) return;   // nothing ran before: there is no list
+    const int nlong = min(*long_count, kFixMaxLong);
+    for (int b = blockIdx.x; b < nlong; b += gridDim.x) {
+        const int first = long_first[b];
+        const int r = carry_row[first];
+        if (threadIdx.x == 0) s_end = nslots;
+        __syncthreads();
+        for (int base = first; base < nslots; base += 256) {   // first slot of another row, 256 slots at a time
+            const int j = base + threadIdx.x;
+            const bool other = j < nslots && carry_row[j] >= 0 && carry_row[j] != r;
+            if (other) atomicMin(&s_end, j);
+            __syncthreads();
+            if (s_end < nslots) break;
+        }
+        __syncthreads();
+        const int end = s_end;
+        const int len = end - first, per = (len + 255) / 256;
+        V acc = V(0);
+        const int a = first + threadIdx.x * per, z = min(a + per, end);
+        for (int j = a; j < z; ++j)
+            if (carry_row[j] == r) acc = add_rn(acc, carry_val[j]);
+        // combine in thread order: warp shuffles (down), then the 8 warp results
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const V t = __shfl_down_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) % (2 * o) == 0) acc = add_rn(acc, t);
+        }
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            V tot = s_part[0];
+            for (int w = 1; w < 8; ++w) tot = add_rn(tot, s_part[w]);
+            y[r] = add_rn(y[r], tot);
+        }
+        __syncthreads();
+    }
 }
 
 template <typename V>
@@ -611,7 +676,7 @@ static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* 
     }
     if (nnz <= 0 || nrow <= 0) return 0;
     const int nruns = merge_runs(nrow, nnz);
-    int* crow = static_cast<int*>(scratch(sizeof(int) * 2 * (size_t)nruns, 2));
+    int* crow = static_cast<int*>(scratch(sizeof(int) * (2 * (size_t)nruns + 2 + kFixMaxLong), 2));
     V* cval = static_cast<V*>(scratch(sizeof(V) * 2 * (size_t)nruns, 3));
     if (!crow || !cval) return 1;
     if (!part) {   // no plan: partition on the fly
@@ -626,7 +691,11 @@ static int run_merge(int nrow, int nnz, const int* rp, const int* col, const V* 
     if (vec) csr_merge_kernel<V, true><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns, stale);
     else csr_merge_kernel<V, false><<<grid, block, 0, s>>>(nrow, nnz, rp, col, val, x, y, pr, pe, crow, cval, nruns, stale);
     THSP_LAUNCH_CHECK();
-    csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y, rp, nrow, nnz, stale);
+    int* long_count = crow + 2 * (size_t)nruns;   // number of long chains (+ one spare word); zeroed by the main kernel
+    int* long_first = long_count + 2;
+    csr_merge_fixup_kernel<V><<<div_up(2 * nruns, 256), 256, 0, s>>>(2 * nruns, crow, cval, y, rp, nrow, nnz, stale, long_count, long_first);
+    THSP_LAUNCH_CHECK();
+    csr_merge_fixup_long_kernel<V><<<std::min(kFixMaxLong, sm_count() * 4), 256, 0, s>>>(2 * nruns, crow, cval, y, long_count, long_first, rp, nrow, nnz, stale);
     THSP_LAUNCH_CHECK();
     return 0;
 }
