@@ -21,6 +21,8 @@
 //         the same forms and the same order, reproduces every iterate bit for bit when the SpMV kernel keeps the
 //         reference's order (stream / scalar).
 // Everything is HBM-bound: a SymGS sweep reads the matrix twice (forward + backward), a CG iteration once.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -103,6 +105,63 @@ __global__ void __launch_bounds__(256) color_resolve_kernel(int nrow, const int*
         if (unew != vnew) atomicOr(forbid + (unew ? u : v), 1ull << cv);
     }
 }
+// ---- first attempt: the greedy colouring in NATURAL row order, as a fixed-point iteration --------------------------------
+// colour(v) = smallest colour no lower-numbered neighbour has.  That rule has exactly one solution (row 0 first, then
+// row 1, ...), which is what a serial greedy pass would produce, and chaotic iteration reaches it: a row is right as soon
+// as its lower neighbours are.  A row recomputes only when a lower neighbour changed in the previous round (`dirty`), so
+// the work is a wave that crosses the matrix once.  Why bother: on matrices from regular grids this is the parity
+// colouring - 8 colours for a 27-point stencil where the hash-ordered colouring below needs 19 - and the rows of a colour
+// are every other grid point, so that the rows of a 32-row tile of the permuted matrix still gather from x lines they
+// share (profiles/r02_solvers.txt: the sweep went from 6.2 to ... ms).  Deep dependency chains (a tridiagonal matrix needs
+// as many rounds as it has rows) stop at a round limit; what is then inconsistent is repaired by the rounds below.
+__global__ void __launch_bounds__(256) color_natural_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
+                                                            int* color, const unsigned char* __restrict__ dirty_in,
+                                                            unsigned char* __restrict__ dirty_out, int* __restrict__ counters)
+{
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    int changed = 0;
+    if (v < nrow && dirty_in[v]) {
+        unsigned long long used = 0ull;
+        const int e0 = rp[v], e1 = rp[v + 1];
+        for (int p = e0; p < e1; ++p) {
+            const int u = ci[p];
+            if (u >= 0 && u < v) used |= 1ull << color[u];
+        }
+        int c = __ffsll((long long)~used) - 1;
+        if (c < 0) {
+            counters[1] = 1;   // more than 64 colours: give this attempt up
+            c = 63;
+        }
+        if (c != color[v]) {
+            color[v] = c;
+            changed = 1;
+            for (int p = e0; p < e1; ++p) {
+                const int w = ci[p];
+                if (w > v && w < nrow) dirty_out[w] = 1;
+            }
+        }
+    }
+    const int any = __syncthreads_count(changed);
+    if (threadIdx.x == 0 && any) atomicAdd(counters, any);
+}
+// after the natural-order attempt: an entry (v, u) whose ends share a colour sends the higher-numbered one back (it is
+// the one that failed to avoid the other: it cannot see it, or the iteration was cut short) and tells it what to avoid
+__global__ void __launch_bounds__(256) color_verify_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
+                                                           const int* __restrict__ color, int* __restrict__ redo,
+                                                           unsigned long long* __restrict__ forbid)
+{
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= nrow) return;
+    const int cv = color[v];
+    for (int p = rp[v]; p < rp[v + 1]; ++p) {
+        const int u = ci[p];
+        if (u == v || u < 0 || u >= nrow || color[u] != cv) continue;
+        const int loser = u > v ? u : v;
+        redo[loser] = 1;
+        atomicOr(forbid + loser, 1ull << cv);
+    }
+}
+
 __global__ void __launch_bounds__(256) color_apply_kernel(int nrow, const int* __restrict__ cout, int* __restrict__ redo,
                                                           int* __restrict__ cin, int* __restrict__ left)
 {
@@ -241,7 +300,7 @@ static inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>((int64_t)
 using namespace thsp;
 
 struct thsp_symgs_plan {
-    int nrow = 0, ncolors = 0, rounds = 0;
+    int nrow = 0, ncolors = 0, rounds = 0, natural_rounds = 0;
     int* perm = nullptr;            // device: rows grouped by colour, ascending inside a colour
     int* color = nullptr;           // device: colour of every row
     std::vector<int> color_ptr;     // host: [ncolors + 1]
@@ -310,10 +369,46 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
     THSP_CUDA(cudaMalloc(&cout, sizeof(int) * ((size_t)nrow + 1)));
     THSP_CUDA(cudaMalloc(&redo, sizeof(int) * ((size_t)nrow + 1)));
     THSP_CUDA(cudaMalloc(&small, sizeof(int) * 4));
-    THSP_CUDA(cudaMemsetAsync(cin, 0xff, sizeof(int) * (size_t)nrow, s));
     THSP_CUDA(cudaMemsetAsync(redo, 0, sizeof(int) * ((size_t)nrow + 1), s));
     const int grid = div_up(nrow, 256);
     int rc = 0;
+    {   // natural-order greedy as a fixed point (color_natural_kernel); whatever it leaves inconsistent goes back to -1
+        static const int env_cap = getenv("THSP_COLOR_NATURAL_ROUNDS") ? atoi(getenv("THSP_COLOR_NATURAL_ROUNDS")) : -1;
+        const int cap = env_cap >= 0 ? env_cap : 4096;
+        unsigned char* dirty = nullptr;
+        THSP_CUDA(cudaMalloc(&dirty, 2 * (size_t)nrow));
+        THSP_CUDA(cudaMemsetAsync(cin, 0, sizeof(int) * (size_t)nrow, s));
+        THSP_CUDA(cudaMemsetAsync(dirty, 1, (size_t)nrow, s));
+        bool gave_up = cap == 0;
+        for (int round = 0; round < cap; ++round) {
+            unsigned char* din = dirty + (size_t)(round & 1) * nrow;
+            unsigned char* dout = dirty + (size_t)((round + 1) & 1) * nrow;
+            THSP_CUDA(cudaMemsetAsync(dout, 0, (size_t)nrow, s));
+            THSP_CUDA(cudaMemsetAsync(small, 0, sizeof(int) * 4, s));
+            color_natural_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, din, dout, small);
+            THSP_LAUNCH_CHECK();
+            p->natural_rounds = round + 1;
+            if ((round & 7) == 7 || round + 1 == cap) {   // look at the counters every eighth round only
+                int h[2] = {0, 0};
+                THSP_CUDA(cudaMemcpyAsync(h, small, sizeof(h), cudaMemcpyDeviceToHost, s));
+                THSP_CUDA(cudaStreamSynchronize(s));
+                if (h[1]) { gave_up = true; break; }
+                if (h[0] == 0) break;
+            }
+        }
+        cudaFree(dirty);
+        if (gave_up) {
+            THSP_CUDA(cudaMemsetAsync(cin, 0xff, sizeof(int) * (size_t)nrow, s));
+            p->natural_rounds = 0;
+        } else {
+            color_verify_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, redo, forbid);
+            THSP_LAUNCH_CHECK();
+            THSP_CUDA(cudaMemcpyAsync(cout, cin, sizeof(int) * (size_t)nrow, cudaMemcpyDeviceToDevice, s));
+            THSP_CUDA(cudaMemsetAsync(small, 0, sizeof(int) * 4, s));
+            color_apply_kernel<<<grid, 256, 0, s>>>(nrow, cout, redo, cin, small);
+            THSP_LAUNCH_CHECK();
+        }
+    }
     for (int round = 0; round < 200; ++round) {
         THSP_CUDA(cudaMemsetAsync(small, 0, sizeof(int) * 4, s));
         color_assign_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, cout, small + 1, forbid);
@@ -401,7 +496,7 @@ int thsp_symgs_plan_info(const thsp_symgs_plan* p, int* ncolors, int* rounds, in
 {
     THSP_REQUIRE(p != nullptr, "null plan");
     if (ncolors) *ncolors = p->ncolors;
-    if (rounds) *rounds = p->rounds;
+    if (rounds) *rounds = p->natural_rounds + p->rounds;
     if (color_ptr_host)
         for (int c = 0; c <= p->ncolors && c < capacity; ++c) color_ptr_host[c] = p->color_ptr[c];
     if (perm_dev) *perm_dev = p->perm;

@@ -37,9 +37,26 @@ sys.path.insert(0, ROOT)
 
 METRIC = "csr_spmv_gflops"
 UNIT = "GFLOP/s"
-# DRAM bytes of one csr_stream_kernel<double> launch on the 256^3 stencil, from the committed ncu capture
-# (5.751718 GB read + 115.587 MB written) - 1.0007x the algorithmic 5,863,223,204 bytes.
-NCU_TRAFFIC_BYTES = 5751718000 + 115587072
+
+
+def ncu_traffic(n):
+    """DRAM bytes of one launch of the timed kernel from the committed ncu capture (profiles/traffic.json, written by
+    scripts/record_traffic.py) - quoted only while the kernel's sources are the ones that were profiled: a capture of
+    an older kernel is reported as null, not as a number that silently went stale."""
+    import hashlib
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        h = hashlib.sha256()
+        for p in t["sources"]:
+            h.update(open(os.path.join(ROOT, p), "rb").read())
+        if h.hexdigest() != t["sources_sha256"]:
+            return None, f"profiles/{t['capture']} was taken from an older version of {', '.join(t['sources'])}: not quoted"
+        if t["grid"] != n:
+            return None, f"the capture is of the {t['grid']}^3 matrix"
+        return int(t["dram_bytes_per_launch"]), f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch ({t['capture']}, same sources by SHA-256); not measurable live"
+    except (OSError, KeyError, ValueError):
+        return None, "no capture recorded (profiles/traffic.json)"
+
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -287,6 +304,7 @@ def run_single(args):
     bytes_alg = csr_bytes(N, N, nnz, True)
     achieved = bytes_alg / (ms * 1e-3) / 1e9
     peak, peak_kind = peak_hbm()
+    traffic, traffic_note = ncu_traffic(n) if kname == "stream" else (None, "the capture is of the stream kernel")
 
     # ---- end to end: host x in, host y out, through the C ABI (copies inside the timed region)
     xh = torch.empty(N, dtype=torch.float64).pin_memory()
@@ -421,9 +439,7 @@ def run_single(args):
                    "rows": N, "nnz": nnz, "kernel": kname, "lanes": lanes, "cache": "inputs (5.9 GB) larger than L2 (126 MB)",
                    "step_ms_min": round(min(per), 5), "step_ms_max": round(max(per), 5)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": NCU_TRAFFIC_BYTES if (n == 256 and kname == "stream") else None,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one csr_stream_kernel launch "
-                                       "(profiles/r01_ncu_stream_final.txt); not measurable live", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": bytes_alg, "frac_of_8TBs_spec": round(achieved / 8000.0, 4)},
         "e2e": {"value": round(e2e_gflops, 2), "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 8,
                 "ms_per_step": round(e2e_ms, 4), "call": "thsp_csr_plan_spmv_host_f64 (pinned x in, y out)"},
@@ -547,7 +563,7 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=20)
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="N>1: SMs the interior SpMV leaves free for the concurrent NCCL all-gather (-1 = 16*log2(N): 16/32/48)")
-    ap.add_argument("--exchange", default="xchg,allgather,halo",
+    ap.add_argument("--exchange", default="xchg,allgather,cepush,halo",
                     help="x refresh modes to time at N>1 (also: cepush, push, fused); the first that works is `value`")
     ap.add_argument("--no-overlap", action="store_true", help="do not overlap interior rows with the x refresh")
     ap.add_argument("--no-preflight", action="store_true", help="N>1: skip the small partitioned-path checks before the timed runs")
