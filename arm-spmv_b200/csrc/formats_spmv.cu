@@ -110,46 +110,67 @@ static int launch_ell(int nrow, int width, const int* col, const V* val, const V
 static constexpr int kCooIPT = 16;   // entries owned by a lane
 
 // kProducts: `val` already holds the products val*x (phase 2 of the two-phase path below); col and x are not read.
+// The CTAs are persistent and keep the first kCooLow rows of y in shared memory across all their blocks of entries,
+// flushed once at the end - for the same reason as the CSC kernel further down: the hub rows of degree-sorted and
+// R-MAT-like matrices sit at the head of the numbering, and every update of a hub row is an atomic on one address that
+// the L2 serialises (R-MAT: 5.7 ms with all updates going to L2).
+static constexpr int kCooLow = 4096;
+
 template <bool kVec, bool kProducts>
-__global__ void __launch_bounds__(256) coo_kernel(int nnz, const int* __restrict__ row, const int* __restrict__ col,
+__global__ void __launch_bounds__(256) coo_kernel(int nnz, int nrow, const int* __restrict__ row, const int* __restrict__ col,
                                                   const double* __restrict__ val, const double* __restrict__ x,
                                                   double* __restrict__ y)
 {
-    const int64_t e64 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kCooIPT;
-    if (e64 >= nnz) return;
-    const int e = (int)e64;
-    const int n = min(kCooIPT, nnz - e);
+    __shared__ double s_low[kCooLow];
+    for (int i = threadIdx.x; i < kCooLow; i += 256) s_low[i] = 0.0;
+    __syncthreads();
     const uint64_t pol = policy_evict_first();
-    int rr[kCooIPT];
-    load_block8<kVec>(row + e, n, rr, pol);
-    load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
-    int cur = rr[0];
-    double sum = 0.0;
+    auto flush = [&](int r, double v) {
+        if (r < kCooLow) atomicAdd(&s_low[r], v);
+        else atomicAdd(y + r, v);
+    };
+    const int64_t nblocks = ((int64_t)nnz + 256 * kCooIPT - 1) / (256 * kCooIPT);
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t e64 = (blk * 256 + threadIdx.x) * kCooIPT;
+        if (e64 >= nnz) continue;
+        const int e = (int)e64;
+        const int n = min(kCooIPT, nnz - e);
+        int rr[kCooIPT];
+        load_block8<kVec>(row + e, n, rr, pol);
+        load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
+        int cur = rr[0];
+        double sum = 0.0;
 #pragma unroll
-    for (int h = 0; h < kCooIPT; h += 8) {
-        int cc[8];
-        double xx[8], vv[8];
-        if (!kProducts) {
-            load_block8<kVec>(col + e + h, n - h, cc, pol);
+        for (int h = 0; h < kCooIPT; h += 8) {
+            int cc[8];
+            double xx[8], vv[8];
+            if (!kProducts) {
+                load_block8<kVec>(col + e + h, n - h, cc, pol);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xx[k] = h + k < n ? ld_gather(x + cc[k]) : 0.0;
-        }
-        load_block8<kVec>(val + e + h, n - h, vv, pol);
+                for (int k = 0; k < 8; ++k) xx[k] = h + k < n ? ld_gather(x + cc[k]) : 0.0;
+            }
+            load_block8<kVec>(val + e + h, n - h, vv, pol);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (h + k < n) {
-                const double p = kProducts ? vv[k] : mul_rn(vv[k], xx[k]);
-                if (rr[h + k] != cur) {
-                    atomicAdd(y + cur, sum);
-                    cur = rr[h + k];
-                    sum = p;
-                } else {
-                    sum = (h + k == 0) ? p : add_rn(sum, p);
+            for (int k = 0; k < 8; ++k) {
+                if (h + k < n) {
+                    const double p = kProducts ? vv[k] : mul_rn(vv[k], xx[k]);
+                    if (rr[h + k] != cur) {
+                        flush(cur, sum);
+                        cur = rr[h + k];
+                        sum = p;
+                    } else {
+                        sum = (h + k == 0) ? p : add_rn(sum, p);
+                    }
                 }
             }
         }
+        flush(cur, sum);
     }
-    atomicAdd(y + cur, sum);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCooLow && i < nrow; i += 256) {
+        const double v = s_low[i];
+        if (v != 0.0) atomicAdd(y + i, v);
+    }
 }
 
 // Two-phase path for a large COO whose rows AND columns jump at random (the 8M x 8M uniform matrix): the fused kernel
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(1024) coo_probe_kernel(int nrow, int nnz, cons
 // Order: unspecified (atomics), like the reference's `omp atomic` scatter (src/mat_vec.cpp:88-91).
 static constexpr int kCscIPT = 16;                       // entries owned by a lane
 static constexpr int kCscChunk = 256 * kCscIPT;          // entries per CTA
-static constexpr int kCscMaxCols = 4096;                 // col_ptr slice kept in shared memory
+static constexpr int kCscMaxCols = 2048;                 // col_ptr slice kept in shared memory
 static constexpr int kCscWin = 2048;
 
 __global__ void __launch_bounds__(256) csc_partition_kernel(int ncol, int nnz, const int* __restrict__ col_ptr, int nchunks,
@@ -236,71 +257,89 @@ __global__ void __launch_bounds__(256) csc_partition_kernel(int ncol, int nnz, c
     part[t] = lo;
 }
 
+// The CTAs are persistent (a few per SM, each walking chunks b, b + grid, ...) for the sake of one more window: the
+// first kCscLow rows of y, kept in shared memory across ALL of a CTA's chunks and flushed once at the end.  Degree-sorted
+// and R-MAT-like matrices keep their hub rows at the head of the numbering; every update of a hub row is an atomic on
+// ONE address, which the L2 serialises (row 0 of the R-MAT matrix receives 370 k of them: that, not bandwidth, held the
+// entry-balanced kernel at 5.4 ms).  Through the window a hub row costs one global atomic per CTA instead.
+static constexpr int kCscLow = 2048;
+
 template <bool kVec>
 __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, const int* __restrict__ col_ptr,
                                                   const int* __restrict__ row, const double* __restrict__ val,
                                                   const double* __restrict__ x, double* __restrict__ y,
-                                                  const int* __restrict__ part)
+                                                  const int* __restrict__ part, int nchunks)
 {
     __shared__ int s_cp[kCscMaxCols + 2];
     __shared__ double s_win[kCscWin];
-    const int e0 = blockIdx.x * kCscChunk;
-    const int e1 = min(e0 + kCscChunk, nnz);
-    const int c_lo = __ldg(part + blockIdx.x);
-    const int c_hi = min(__ldg(part + blockIdx.x + 1), ncol - 1);   // column of the first entry of the next chunk
-    const int span = c_hi - c_lo + 1;                               // columns that may hold entries of this chunk
-    const bool in_smem = span <= kCscMaxCols;
-    if (in_smem)
-        for (int i = threadIdx.x; i <= span; i += 256) s_cp[i] = __ldg(col_ptr + c_lo + i);
-    for (int i = threadIdx.x; i < kCscWin; i += 256) s_win[i] = 0.0;
-    __syncthreads();
-    int w0 = c_lo + span / 2 - kCscWin / 2;
-    w0 = max(0, min(w0, nrow - kCscWin));
+    __shared__ double s_low[kCscLow];
+    for (int i = threadIdx.x; i < kCscLow; i += 256) s_low[i] = 0.0;
     const uint64_t pol = policy_evict_first();   // row_ind / val are read once: leave L2 to y
-    const int e = e0 + threadIdx.x * kCscIPT;
-    if (e < e1) {
-        const int n = min(kCscIPT, e1 - e);
-        int rr[kCscIPT];
-        load_block8<kVec>(row + e, n, rr, pol);
-        load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
-        // column of the lane's first entry: last c in [c_lo, c_hi] with col_ptr[c] <= e
-        int lo = 0, hi = span;   // cp[lo] <= e < cp[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            const int v = in_smem ? s_cp[mid] : __ldg(col_ptr + c_lo + mid);
-            if (v <= e) lo = mid; else hi = mid;
-        }
-        int c = lo;
-        int next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
-        double xc = ld_gather(x + c_lo + c);
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int e0 = chunk * kCscChunk;
+        const int e1 = min(e0 + kCscChunk, nnz);
+        const int c_lo = __ldg(part + chunk);
+        const int c_hi = min(__ldg(part + chunk + 1), ncol - 1);   // column of the first entry of the next chunk
+        const int span = c_hi - c_lo + 1;                               // columns that may hold entries of this chunk
+        const bool in_smem = span <= kCscMaxCols;
+        __syncthreads();   // the previous chunk's flush is done with s_cp / s_win
+        if (in_smem)
+            for (int i = threadIdx.x; i <= span; i += 256) s_cp[i] = __ldg(col_ptr + c_lo + i);
+        for (int i = threadIdx.x; i < kCscWin; i += 256) s_win[i] = 0.0;
+        __syncthreads();
+        int w0 = c_lo + span / 2 - kCscWin / 2;
+        w0 = max(kCscLow, min(w0, nrow - kCscWin));   // below kCscLow the other window is in charge
+        const int e = e0 + threadIdx.x * kCscIPT;
+        if (e < e1) {
+            const int n = min(kCscIPT, e1 - e);
+            int rr[kCscIPT];
+            load_block8<kVec>(row + e, n, rr, pol);
+            load_block8<kVec>(row + e + 8, n - 8, rr + 8, pol);
+            // column of the lane's first entry: last c in [c_lo, c_hi] with col_ptr[c] <= e
+            int lo = 0, hi = span;   // cp[lo] <= e < cp[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                const int v = in_smem ? s_cp[mid] : __ldg(col_ptr + c_lo + mid);
+                if (v <= e) lo = mid; else hi = mid;
+            }
+            int c = lo;
+            int next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
+            double xc = ld_gather(x + c_lo + c);
 #pragma unroll
-        for (int h = 0; h < kCscIPT; h += 8) {
-            double vv[8];
-            load_block8<kVec>(val + e + h, n - h, vv, pol);
+            for (int h = 0; h < kCscIPT; h += 8) {
+                double vv[8];
+                load_block8<kVec>(val + e + h, n - h, vv, pol);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (h + k < n) {
-                    const int g = e + h + k;
-                    if (g >= next) {   // rare: walk over the column boundary (and any empty columns)
-                        do {
-                            ++c;
-                            next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
-                        } while (g >= next);
-                        xc = ld_gather(x + c_lo + c);
+                for (int k = 0; k < 8; ++k) {
+                    if (h + k < n) {
+                        const int g = e + h + k;
+                        if (g >= next) {   // rare: walk over the column boundary (and any empty columns)
+                            do {
+                                ++c;
+                                next = in_smem ? s_cp[c + 1] : __ldg(col_ptr + c_lo + c + 1);
+                            } while (g >= next);
+                            xc = ld_gather(x + c_lo + c);
+                        }
+                        const double p = mul_rn(vv[k], xc);
+                        const int r = rr[h + k];
+                        const int w = r - w0;
+                        if (r < kCscLow) atomicAdd(&s_low[r], p);
+                        else if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
+                        else atomicAdd(y + r, p);
                     }
-                    const double p = mul_rn(vv[k], xc);
-                    const int r = rr[h + k];
-                    const int w = r - w0;
-                    if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
-                    else atomicAdd(y + r, p);
                 }
             }
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kCscWin; i += 256) {
+            const double v = s_win[i];
+            if (v != 0.0 && w0 + i < nrow && w0 + i >= 0) atomicAdd(y + w0 + i, v);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kCscWin; i += 256) {
-        const double v = s_win[i];
-        if (v != 0.0 && w0 + i < nrow) atomicAdd(y + w0 + i, v);
+    for (int i = threadIdx.x; i < kCscLow; i += 256) {
+        const double v = s_low[i];
+        if (v != 0.0 && i < nrow) atomicAdd(y + i, v);
     }
 }
 
@@ -506,16 +545,16 @@ int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row
             const int n = std::min(kCooSlab, nnz - e0);
             coo_product_kernel<<<div_up(n, 2048), 256, 0, s>>>(n, col_ind + e0, val + e0, x, prod);
             THSP_LAUNCH_CHECK();
-            const int grid = div_up(div_up(n, kCooIPT), 256);
-            if (vec) coo_kernel<true, true><<<grid, 256, 0, s>>>(n, row_ind + e0, nullptr, prod, nullptr, y);
-            else coo_kernel<false, true><<<grid, 256, 0, s>>>(n, row_ind + e0, nullptr, prod, nullptr, y);
+            const int grid = std::min(div_up(div_up(n, kCooIPT), 256), sm_count() * 8);
+            if (vec) coo_kernel<true, true><<<grid, 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
+            else coo_kernel<false, true><<<grid, 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
             THSP_LAUNCH_CHECK();
         }
         return 0;
     }
-    const int grid = div_up(div_up(nnz, kCooIPT), 256);
-    if (vec) coo_kernel<true, false><<<grid, 256, 0, s>>>(nnz, row_ind, col_ind, val, x, y);
-    else coo_kernel<false, false><<<grid, 256, 0, s>>>(nnz, row_ind, col_ind, val, x, y);
+    const int grid = std::min(div_up(div_up(nnz, kCooIPT), 256), sm_count() * 8);   // persistent: see coo_kernel
+    if (vec) coo_kernel<true, false><<<grid, 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
+    else coo_kernel<false, false><<<grid, 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -532,8 +571,9 @@ int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int
     csc_partition_kernel<<<div_up(nchunks + 1, 256), 256, 0, s>>>(ncol, nnz, col_ptr, nchunks, part);
     THSP_LAUNCH_CHECK();
     const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads of whole sectors
-    if (vec) csc_kernel<true><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part);
-    else csc_kernel<false><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part);
+    const int grid = std::min(nchunks, sm_count() * 8);   // persistent: a CTA keeps its low-row window across its chunks
+    if (vec) csc_kernel<true><<<grid, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    else csc_kernel<false><<<grid, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
     THSP_LAUNCH_CHECK();
     return 0;
 }

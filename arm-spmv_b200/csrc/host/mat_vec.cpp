@@ -220,7 +220,8 @@ void* COOMatrixMatVectorNumaThread(void* args)
     NumaNode4COO* pn = static_cast<NumaNode4COO*>(args);
     use(pn->alloc);
     // row indices stay global; Y - start_row makes y[row - start_row] of the reference (:500)
-    ok(thsp_coo_spmv_f64(pn->rows_per_node, 0, pn->nnz, pn->sub_row_ind, pn->sub_col_ind, pn->sub_values, pn->X,
+    // (nrow = one past the last global row of the block: the kernel's row bound is on global indices)
+    ok(thsp_coo_spmv_f64(pn->start_row + pn->rows_per_node, 0, pn->nnz, pn->sub_row_ind, pn->sub_col_ind, pn->sub_values, pn->X,
                          pn->Y - pn->start_row, nullptr),
        "COO block SpMV");
     if (!g_driver_syncs) ok(thsp_device_sync(), "device synchronise");

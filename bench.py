@@ -496,6 +496,44 @@ def preflight_multi(rank, world, device):
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
     out["csc_column_blocks_reduce_scatter"] = {"ok": bool(err.item() <= 1e-12), "max_row_error": float(err.item()), "tolerance": 1e-12,
                                                "matrix": f"uniform {n}x{n}, {nnz} entries", "gpus": world}
+    # ---- (1b) the same at a size where time means something: 4M x 4M, 64 M entries, column blocks + reduce-scatter over
+    # NVLink against the whole matrix on one GPU (CSCMatrixMatVector) - the hardware number SURVEY.md 8(f)-3 asks for
+    try:
+        nb, nzb = 1 << 22, 1 << 26
+        Ab = H.uniform_coo(nb, nb, nzb, 43, device=device)
+        Cb = H.CSCMatrix(Ab)
+        del Ab
+        xb = H.gen_vector(nb, 3, device=device)
+        Pb = power.ColumnPartitionedCSC(nb, nb, Cb.col_ptr, Cb.row_ind, Cb.values, rank, world, ops)
+        yb = torch.zeros(Pb.nrow_local, dtype=torch.float64, device=device)
+        xs = xb.values[Pb.c0:Pb.c0 + Pb.ncol_local].clone()
+
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        ms_part = timed(lambda: Pb.spmv(xs, yb))
+        yw = H.Vector(nb, device=device)
+        yw.Fill(0.0)
+        ms_one = timed(lambda: H.CSCMatrixMatVector(Cb, xb, yw))   # every rank runs the whole matrix alone: max = one GPU's time
+        out["csc_column_blocks_timing"] = {"matrix": f"uniform {nb}x{nb}, {nzb} entries", "gpus": world, "ms_per_spmv": round(ms_part, 4),
+                                           "ms_one_gpu_whole_matrix": round(ms_one, 4), "speedup": round(ms_one / ms_part, 3),
+                                           "note": "y = A x with the column blocks on the GPUs and one NCCL reduce-scatter of the partial y's per product"}
+        del Cb, Pb, xb, yb, yw, xs
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["csc_column_blocks_timing"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     # ---- (2) the C++ *MatVectorNuma calls on G = world GPUs (one process drives all of them)
     res = {"ok": None}
     if rank == 0:
