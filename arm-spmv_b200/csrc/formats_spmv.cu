@@ -114,7 +114,7 @@ static constexpr int kCooIPT = 16;   // entries owned by a lane
 // flushed once at the end - for the same reason as the CSC kernel further down: the hub rows of degree-sorted and
 // R-MAT-like matrices sit at the head of the numbering, and every update of a hub row is an atomic on one address that
 // the L2 serialises (R-MAT: 5.7 ms with all updates going to L2).
-static constexpr int kCooLow = 4096;
+static constexpr int kCooLow = 2048;
 
 template <bool kVec, bool kProducts>
 __global__ void __launch_bounds__(256) coo_kernel(int nnz, int nrow, const int* __restrict__ row, const int* __restrict__ col,
@@ -471,6 +471,20 @@ __global__ void __launch_bounds__(768, 1)
 
 using namespace thsp;
 
+// Persistent kernels (COO, CSC): exactly as many CTAs as are resident at once, so that all of them advance together
+// over the entries (one wave; with more CTAs than fit, the later ones start when the earlier ones have finished ALL
+// their blocks and the matrix is swept twice: the sorted 256^3 COO went from 1.61 to 1.88 ms that way).
+template <class K>
+static int resident_ctas(K kernel, int threads)
+{
+    static int per_sm = 0;   // per instantiation (= per kernel); the GPUs of a box are alike
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    return per_sm * sm_count();
+}
+
 extern "C" {
 
 int thsp_ell_spmv_f64(int nrow, int ncol, int width, const int* col_ind, const double* val, const double* x, double* y,
@@ -545,16 +559,16 @@ int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row
             const int n = std::min(kCooSlab, nnz - e0);
             coo_product_kernel<<<div_up(n, 2048), 256, 0, s>>>(n, col_ind + e0, val + e0, x, prod);
             THSP_LAUNCH_CHECK();
-            const int grid = std::min(div_up(div_up(n, kCooIPT), 256), sm_count() * 8);
-            if (vec) coo_kernel<true, true><<<grid, 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
-            else coo_kernel<false, true><<<grid, 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
+            const int want = div_up(div_up(n, kCooIPT), 256);
+            if (vec) coo_kernel<true, true><<<std::min(want, resident_ctas(coo_kernel<true, true>, 256)), 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
+            else coo_kernel<false, true><<<std::min(want, resident_ctas(coo_kernel<false, true>, 256)), 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
             THSP_LAUNCH_CHECK();
         }
         return 0;
     }
-    const int grid = std::min(div_up(div_up(nnz, kCooIPT), 256), sm_count() * 8);   // persistent: see coo_kernel
-    if (vec) coo_kernel<true, false><<<grid, 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
-    else coo_kernel<false, false><<<grid, 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
+    const int want = div_up(div_up(nnz, kCooIPT), 256);   // persistent: see coo_kernel
+    if (vec) coo_kernel<true, false><<<std::min(want, resident_ctas(coo_kernel<true, false>, 256)), 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
+    else coo_kernel<false, false><<<std::min(want, resident_ctas(coo_kernel<false, false>, 256)), 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -571,9 +585,9 @@ int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int
     csc_partition_kernel<<<div_up(nchunks + 1, 256), 256, 0, s>>>(ncol, nnz, col_ptr, nchunks, part);
     THSP_LAUNCH_CHECK();
     const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads of whole sectors
-    const int grid = std::min(nchunks, sm_count() * 8);   // persistent: a CTA keeps its low-row window across its chunks
-    if (vec) csc_kernel<true><<<grid, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
-    else csc_kernel<false><<<grid, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    // persistent: a CTA keeps its low-row window across its chunks
+    if (vec) csc_kernel<true><<<std::min(nchunks, resident_ctas(csc_kernel<true>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    else csc_kernel<false><<<std::min(nchunks, resident_ctas(csc_kernel<false>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
     THSP_LAUNCH_CHECK();
     return 0;
 }

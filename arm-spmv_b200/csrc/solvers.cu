@@ -115,34 +115,41 @@ __global__ void __launch_bounds__(256) color_resolve_kernel(int nrow, const int*
 // share (profiles/r02_solvers.txt: the sweep went from 6.2 to ... ms).  Deep dependency chains (a tridiagonal matrix needs
 // as many rounds as it has rows) stop at a round limit; what is then inconsistent is repaired by the rounds below.
 __global__ void __launch_bounds__(256) color_natural_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
-                                                            int* color, const unsigned char* __restrict__ dirty_in,
-                                                            unsigned char* __restrict__ dirty_out, int* __restrict__ counters)
+                                                            int* color, unsigned* dirty_in, unsigned char* __restrict__ dirty_out,
+                                                            int* __restrict__ counters, int slot)
 {
-    const int v = blockIdx.x * 256 + threadIdx.x;
+    // four rows per thread: one 32-bit load tells whether any of them has work (most rounds: none of them)
+    const int t = blockIdx.x * 256 + threadIdx.x;
     int changed = 0;
-    if (v < nrow && dirty_in[v]) {
-        unsigned long long used = 0ull;
-        const int e0 = rp[v], e1 = rp[v + 1];
-        for (int p = e0; p < e1; ++p) {
-            const int u = ci[p];
-            if (u >= 0 && u < v) used |= 1ull << color[u];
-        }
-        int c = __ffsll((long long)~used) - 1;
-        if (c < 0) {
-            counters[1] = 1;   // more than 64 colours: give this attempt up
-            c = 63;
-        }
-        if (c != color[v]) {
-            color[v] = c;
-            changed = 1;
+    const unsigned w = 4 * t < nrow ? dirty_in[t] : 0u;
+    if (w) {
+        dirty_in[t] = 0u;   // this buffer is the OUTPUT of the round after next: leave it clean
+        for (int b = 0; b < 4; ++b) {
+            const int v = 4 * t + b;
+            if (!((w >> (8 * b)) & 0xffu) || v >= nrow) continue;
+            unsigned long long used = 0ull;
+            const int e0 = rp[v], e1 = rp[v + 1];
             for (int p = e0; p < e1; ++p) {
-                const int w = ci[p];
-                if (w > v && w < nrow) dirty_out[w] = 1;
+                const int u = ci[p];
+                if (u >= 0 && u < v) used |= 1ull << color[u];
+            }
+            int c = __ffsll((long long)~used) - 1;
+            if (c < 0) {
+                counters[1] = 1;   // more than 64 colours: give this attempt up
+                c = 63;
+            }
+            if (c != color[v]) {
+                color[v] = c;
+                changed = 1;
+                for (int p = e0; p < e1; ++p) {
+                    const int x = ci[p];
+                    if (x > v && x < nrow) dirty_out[x] = 1;
+                }
             }
         }
     }
     const int any = __syncthreads_count(changed);
-    if (threadIdx.x == 0 && any) atomicAdd(counters, any);
+    if (threadIdx.x == 0 && any) atomicAdd(counters + 2 + slot, any);
 }
 // after the natural-order attempt: an entry (v, u) whose ends share a colour sends the higher-numbered one back (it is
 // the one that failed to avoid the other: it cannot see it, or the iteration was cut short) and tells it what to avoid
@@ -376,26 +383,32 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
         static const int env_cap = getenv("THSP_COLOR_NATURAL_ROUNDS") ? atoi(getenv("THSP_COLOR_NATURAL_ROUNDS")) : -1;
         const int cap = env_cap >= 0 ? env_cap : 4096;
         unsigned char* dirty = nullptr;
-        THSP_CUDA(cudaMalloc(&dirty, 2 * (size_t)nrow));
+        const size_t dbytes = (((size_t)nrow + 3) & ~(size_t)3) + 256;   // each buffer a whole number of 32-bit words
+        int* cnt = nullptr;
+        THSP_CUDA(cudaMalloc(&dirty, 2 * dbytes));
+        THSP_CUDA(cudaMalloc(&cnt, sizeof(int) * 16));
         THSP_CUDA(cudaMemsetAsync(cin, 0, sizeof(int) * (size_t)nrow, s));
-        THSP_CUDA(cudaMemsetAsync(dirty, 1, (size_t)nrow, s));
+        THSP_CUDA(cudaMemsetAsync(dirty, 1, dbytes, s));            // round 0: every row computes
+        THSP_CUDA(cudaMemsetAsync(dirty + dbytes, 0, dbytes, s));
+        THSP_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 16, s));
         bool gave_up = cap == 0;
+        const int grid4 = div_up(div_up(nrow, 4), 256);
         for (int round = 0; round < cap; ++round) {
-            unsigned char* din = dirty + (size_t)(round & 1) * nrow;
-            unsigned char* dout = dirty + (size_t)((round + 1) & 1) * nrow;
-            THSP_CUDA(cudaMemsetAsync(dout, 0, (size_t)nrow, s));
-            THSP_CUDA(cudaMemsetAsync(small, 0, sizeof(int) * 4, s));
-            color_natural_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, din, dout, small);
+            unsigned char* din = dirty + (size_t)(round & 1) * dbytes;
+            unsigned char* dout = dirty + (size_t)((round + 1) & 1) * dbytes;
+            color_natural_kernel<<<grid4, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, reinterpret_cast<unsigned*>(din), dout, cnt, round & 7);
             THSP_LAUNCH_CHECK();
             p->natural_rounds = round + 1;
             if ((round & 7) == 7 || round + 1 == cap) {   // look at the counters every eighth round only
-                int h[2] = {0, 0};
-                THSP_CUDA(cudaMemcpyAsync(h, small, sizeof(h), cudaMemcpyDeviceToHost, s));
+                int h[10];
+                THSP_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+                THSP_CUDA(cudaMemsetAsync(cnt + 2, 0, sizeof(int) * 8, s));
                 THSP_CUDA(cudaStreamSynchronize(s));
                 if (h[1]) { gave_up = true; break; }
-                if (h[0] == 0) break;
+                if (h[2 + (round & 7)] == 0) break;   // the last round changed nothing: nothing is dirty, the fixed point is reached
             }
         }
+        cudaFree(cnt);
         cudaFree(dirty);
         if (gave_up) {
             THSP_CUDA(cudaMemsetAsync(cin, 0xff, sizeof(int) * (size_t)nrow, s));

@@ -35,9 +35,15 @@ if which == "stencil":      # configs[1]: 27-point stencil 256^3, every format
     D = H.DIAMatrix(B); prof(lambda: H.DIAMatrixMatVector(D, x, y)); del D
     A = H.stencil27_coo(n); prof(lambda: H.COOMatirxMatVector(A, x, y))
     Cc = H.CSCMatrix(A); prof(lambda: H.CSCMatrixMatVector(Cc, x, y))
+    del A, Cc
+    from arm_spmv_b200 import solvers                                # SymGS: every colour of one forward + backward sweep
+    S = solvers.SymGS(B)
+    r = H.gen_vector(N, 5)
+    S.sweep(r, y)
+    prof(lambda: S.sweep(r, y))
 elif which == "rmat":       # configs[2]
     A = H.rmat_coo(24, 16 << 24, 42)
-    B = H.CSRMatrix(A); del A
+    B = H.CSRMatrix(A)
     x = H.gen_vector(B.ncol, 3)
     y = H.Vector(B.nrow); y.Fill(0.0)
     B.plan()
@@ -47,6 +53,9 @@ elif which == "rmat":       # configs[2]
     y32 = torch.zeros(B.nrow, dtype=torch.float32, device="cuda")
     x32 = x.values.to(torch.float32)
     prof(lambda: H.csr_spmv_kernel(4, 1, B32, x32, y32))
+    del B32, y32, x32
+    prof(lambda: H.COOMatirxMatVector(A, x, y))                    # coo_kernel with the head-row window
+    Cc = H.CSCMatrix(A); prof(lambda: H.CSCMatrixMatVector(Cc, x, y))
 else:                       # configs[3]
     A = H.uniform_coo(1 << 23, 1 << 23, 1 << 27, 43)
     x = H.gen_vector(A.ncol, 3)
