@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -116,17 +117,22 @@ static constexpr int kCooIPT = 16;   // entries owned by a lane
 // the L2 serialises (R-MAT: 5.7 ms with all updates going to L2).
 static constexpr int kCooLow = 2048;
 
-template <bool kVec, bool kProducts>
+// kWin = false is the plain one-shot kernel (a CTA per 4096 entries, every update straight to y): the window costs the
+// sorted 256^3 stencil 16 % (1.61 -> 1.87 ms) and buys nothing there, so it is only switched on when a probe of the row
+// indices finds the head of the numbering over-represented (head_heavy below).
+template <bool kVec, bool kProducts, bool kWin>
 __global__ void __launch_bounds__(256) coo_kernel(int nnz, int nrow, const int* __restrict__ row, const int* __restrict__ col,
                                                   const double* __restrict__ val, const double* __restrict__ x,
                                                   double* __restrict__ y)
 {
-    __shared__ double s_low[kCooLow];
-    for (int i = threadIdx.x; i < kCooLow; i += 256) s_low[i] = 0.0;
-    __syncthreads();
+    __shared__ double s_low[kWin ? kCooLow : 1];
+    if (kWin) {
+        for (int i = threadIdx.x; i < kCooLow; i += 256) s_low[i] = 0.0;
+        __syncthreads();
+    }
     const uint64_t pol = policy_evict_first();
     auto flush = [&](int r, double v) {
-        if (r < kCooLow) atomicAdd(&s_low[r], v);
+        if (kWin && r < kCooLow) atomicAdd(&s_low[r], v);
         else atomicAdd(y + r, v);
     };
     const int64_t nblocks = ((int64_t)nnz + 256 * kCooIPT - 1) / (256 * kCooIPT);
@@ -166,10 +172,12 @@ __global__ void __launch_bounds__(256) coo_kernel(int nnz, int nrow, const int* 
         }
         flush(cur, sum);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kCooLow && i < nrow; i += 256) {
-        const double v = s_low[i];
-        if (v != 0.0) atomicAdd(y + i, v);
+    if (kWin) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kCooLow && i < nrow; i += 256) {
+            const double v = s_low[i];
+            if (v != 0.0) atomicAdd(y + i, v);
+        }
     }
 }
 
@@ -212,10 +220,12 @@ __global__ void __launch_bounds__(1024) coo_probe_kernel(int nrow, int nnz, cons
     const int jr = __syncthreads_count(dr < 0 || dr > 4096);
     const int jc = __syncthreads_count(dc < 0 || dc > 4096);
     const int head = __syncthreads_count(r < nrow / 64);
+    const int low = __syncthreads_count(r < kCooLow);
     if (threadIdx.x == 0) {
         out[0] = jr;
         out[1] = jc;
         out[2] = head;
+        out[3] = low;
     }
 }
 
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(1024) coo_probe_kernel(int nrow, int nnz, cons
 // Order: unspecified (atomics), like the reference's `omp atomic` scatter (src/mat_vec.cpp:88-91).
 static constexpr int kCscIPT = 16;                       // entries owned by a lane
 static constexpr int kCscChunk = 256 * kCscIPT;          // entries per CTA
-static constexpr int kCscMaxCols = 2048;                 // col_ptr slice kept in shared memory
+static constexpr int kCscMaxCols = 4096;                 // col_ptr slice kept in shared memory
 static constexpr int kCscWin = 2048;
 
 __global__ void __launch_bounds__(256) csc_partition_kernel(int ncol, int nnz, const int* __restrict__ col_ptr, int nchunks,
@@ -264,16 +274,20 @@ __global__ void __launch_bounds__(256) csc_partition_kernel(int ncol, int nnz, c
 // entry-balanced kernel at 5.4 ms).  Through the window a hub row costs one global atomic per CTA instead.
 static constexpr int kCscLow = 2048;
 
-template <bool kVec>
+// kLow = false: a CTA per chunk, no head-row window (it costs the stencil and the uniform matrix 5-12 % and is switched on
+// only when a probe of row_ind finds the head of the numbering over-represented).
+template <bool kVec, bool kLow>
 __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, const int* __restrict__ col_ptr,
                                                   const int* __restrict__ row, const double* __restrict__ val,
                                                   const double* __restrict__ x, double* __restrict__ y,
                                                   const int* __restrict__ part, int nchunks)
 {
-    __shared__ int s_cp[kCscMaxCols + 2];
+    constexpr int kMaxCols = kLow ? kCscMaxCols / 2 : kCscMaxCols;   // 48 KB of static shared memory for all three arrays
+    __shared__ int s_cp[kMaxCols + 2];
     __shared__ double s_win[kCscWin];
-    __shared__ double s_low[kCscLow];
-    for (int i = threadIdx.x; i < kCscLow; i += 256) s_low[i] = 0.0;
+    __shared__ double s_low[kLow ? kCscLow : 1];
+    if (kLow)
+        for (int i = threadIdx.x; i < kCscLow; i += 256) s_low[i] = 0.0;
     const uint64_t pol = policy_evict_first();   // row_ind / val are read once: leave L2 to y
     for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int e0 = chunk * kCscChunk;
@@ -281,14 +295,14 @@ __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, c
         const int c_lo = __ldg(part + chunk);
         const int c_hi = min(__ldg(part + chunk + 1), ncol - 1);   // column of the first entry of the next chunk
         const int span = c_hi - c_lo + 1;                               // columns that may hold entries of this chunk
-        const bool in_smem = span <= kCscMaxCols;
+        const bool in_smem = span <= kMaxCols;
         __syncthreads();   // the previous chunk's flush is done with s_cp / s_win
         if (in_smem)
             for (int i = threadIdx.x; i <= span; i += 256) s_cp[i] = __ldg(col_ptr + c_lo + i);
         for (int i = threadIdx.x; i < kCscWin; i += 256) s_win[i] = 0.0;
         __syncthreads();
         int w0 = c_lo + span / 2 - kCscWin / 2;
-        w0 = max(kCscLow, min(w0, nrow - kCscWin));   // below kCscLow the other window is in charge
+        w0 = max(kLow ? kCscLow : 0, min(w0, nrow - kCscWin));   // below kCscLow the other window is in charge
         const int e = e0 + threadIdx.x * kCscIPT;
         if (e < e1) {
             const int n = min(kCscIPT, e1 - e);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, c
                         const double p = mul_rn(vv[k], xc);
                         const int r = rr[h + k];
                         const int w = r - w0;
-                        if (r < kCscLow) atomicAdd(&s_low[r], p);
+                        if (kLow && r < kCscLow) atomicAdd(&s_low[r], p);
                         else if (w >= 0 && w < kCscWin) atomicAdd(&s_win[w], p);
                         else atomicAdd(y + r, p);
                     }
@@ -336,11 +350,21 @@ __global__ void __launch_bounds__(256) csc_kernel(int nrow, int ncol, int nnz, c
             if (v != 0.0 && w0 + i < nrow && w0 + i >= 0) atomicAdd(y + w0 + i, v);
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kCscLow; i += 256) {
-        const double v = s_low[i];
-        if (v != 0.0 && i < nrow) atomicAdd(y + i, v);
+    if (kLow) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kCscLow; i += 256) {
+            const double v = s_low[i];
+            if (v != 0.0 && i < nrow) atomicAdd(y + i, v);
+        }
     }
+}
+
+// 1024 row indices spread over the entries: how many lie below `low`?
+__global__ void __launch_bounds__(1024) head_probe_kernel(int nnz, const int* __restrict__ row, int low, int* __restrict__ out)
+{
+    const int64_t i = (int64_t)threadIdx.x * (nnz - 1) / 1023;
+    const int c = __syncthreads_count(row[i] < low);
+    if (threadIdx.x == 0) out[0] = c;
 }
 
 // ============================================================================ DIA ==========
@@ -510,28 +534,67 @@ int thsp_ell_spmv_f32(int nrow, int ncol, int width, const int* col_ind, const f
                : launch_ell<float, 1>(nrow, width, col_ind, val, x, y, s);
 }
 
-// Does this COO jump at random in both index arrays, without hub rows?  Probed once per (array, size) and remembered: both paths are
-// correct for any input, so a stale answer can only cost time.
-static bool coo_is_scattered(int nrow, int nnz, const int* row_ind, const int* col_ind, cudaStream_t s)
+// Two questions about a COO matrix, answered once per (arrays, size) from 1024 probes and remembered (both kernels
+// are correct for any input, so a stale answer can only cost time): does it jump at random in both index arrays without
+// hub rows (-> products-then-scatter path), and is the head of the row numbering over-represented (-> head-row window)?
+struct CooTraits {
+    bool scattered, head_heavy;
+};
+static bool over_represented(int hits, int low, int nrow)
 {
-    struct Seen { const int* row; const int* col; int nnz; bool scattered; };
+    // hits of 1024 probes below `low`; uniform rows would give 1024 * low / nrow
+    const double expect = 1024.0 * std::min(1.0, (double)low / std::max(nrow, 1));
+    return hits >= 16 && hits > 8.0 * expect;
+}
+static CooTraits coo_traits(int nrow, int nnz, const int* row_ind, const int* col_ind, cudaStream_t s)
+{
+    struct Seen { const int* row; const int* col; int nnz; CooTraits t; };
     static Seen seen[8] = {};
     static int next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     for (const Seen& e : seen)
-        if (e.row == row_ind && e.col == col_ind && e.nnz == nnz) return e.scattered;
-    int* d = static_cast<int*>(scratch(3 * sizeof(int), 1));
-    int h[3] = {0, 0, 0};
-    if (!d) return false;
+        if (e.row == row_ind && e.col == col_ind && e.nnz == nnz) return e.t;
+    CooTraits t{false, false};
+    if (nnz < (1 << 16)) return t;
+    int* d = static_cast<int*>(scratch(4 * sizeof(int), 1));
+    int h[4] = {0, 0, 0, 0};
+    if (!d) return t;
     coo_probe_kernel<<<1, 1024, 0, s>>>(nrow, nnz, row_ind, col_ind, d);
     note_launch();
     if (cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
         cudaGetLastError();
+        return t;
+    }
+    t.scattered = h[0] > 256 && h[1] > 256 && h[2] <= 80;
+    t.head_heavy = over_represented(h[3], kCooLow, nrow);
+    seen[next] = Seen{row_ind, col_ind, nnz, t};
+    next = (next + 1) % 8;
+    return t;
+}
+static bool csc_head_heavy(int nrow, int nnz, const int* row_ind, cudaStream_t s)
+{
+    struct Seen { const int* row; int nnz; bool heavy; };
+    static Seen seen[8] = {};
+    static int next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Seen& e : seen)
+        if (e.row == row_ind && e.nnz == nnz) return e.heavy;
+    if (nnz < (1 << 16)) return false;
+    int* d = static_cast<int*>(scratch(4 * sizeof(int), 1));
+    int h = 0;
+    if (!d) return false;
+    head_probe_kernel<<<1, 1024, 0, s>>>(nnz, row_ind, kCscLow, d);
+    note_launch();
+    if (cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError();
         return false;
     }
-    const bool scattered = h[0] > 256 && h[1] > 256 && h[2] <= 80;
-    seen[next] = Seen{row_ind, col_ind, nnz, scattered};
+    const bool heavy = over_represented(h, kCscLow, nrow);
+    seen[next] = Seen{row_ind, nnz, heavy};
     next = (next + 1) % 8;
-    return scattered;
+    return heavy;
 }
 
 int thsp_coo_spmv_f64(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
@@ -548,10 +611,26 @@ int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row
     if (nnz <= 0) return 0;
     cudaStream_t s = as_stream(stream);
     const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)col_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads
+    const CooTraits traits = coo_traits(nrow, nnz, row_ind, col_ind, s);
     bool two_phase = path > 0;
     if (path < 0)   // x and y together well beyond what L2 keeps of randomly accessed data, enough entries to matter
-        two_phase = nnz >= (1 << 24) && ((size_t)nrow + (size_t)ncol) * sizeof(double) > ((size_t)96 << 20) &&
-                    coo_is_scattered(nrow, nnz, row_ind, col_ind, s);
+        two_phase = nnz >= (1 << 24) && ((size_t)nrow + (size_t)ncol) * sizeof(double) > ((size_t)96 << 20) && traits.scattered;
+    auto launch = [&](int n, const int* ri, const int* ci, const double* va, bool products) -> int {
+        const int want = div_up(div_up(n, kCooIPT), 256);
+#define THSP_COO(V, P, W)                                                                                                   \
+    coo_kernel<V, P, W><<<(W) ? std::min(want, resident_ctas(coo_kernel<V, P, W>, 256)) : want, 256, 0, s>>>(n, nrow, ri, ci, va, x, y)
+        const bool w = traits.head_heavy;
+        if (products) {
+            if (vec) { if (w) THSP_COO(true, true, true); else THSP_COO(true, true, false); }
+            else { if (w) THSP_COO(false, true, true); else THSP_COO(false, true, false); }
+        } else {
+            if (vec) { if (w) THSP_COO(true, false, true); else THSP_COO(true, false, false); }
+            else { if (w) THSP_COO(false, false, true); else THSP_COO(false, false, false); }
+        }
+#undef THSP_COO
+        THSP_LAUNCH_CHECK();
+        return 0;
+    };
     if (two_phase) {
         double* prod = static_cast<double*>(scratch(sizeof(double) * (size_t)std::min(nnz, kCooSlab), 3));
         if (!prod) return 1;
@@ -559,18 +638,11 @@ int thsp_coo_spmv_path_f64(int path, int nrow, int ncol, int nnz, const int* row
             const int n = std::min(kCooSlab, nnz - e0);
             coo_product_kernel<<<div_up(n, 2048), 256, 0, s>>>(n, col_ind + e0, val + e0, x, prod);
             THSP_LAUNCH_CHECK();
-            const int want = div_up(div_up(n, kCooIPT), 256);
-            if (vec) coo_kernel<true, true><<<std::min(want, resident_ctas(coo_kernel<true, true>, 256)), 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
-            else coo_kernel<false, true><<<std::min(want, resident_ctas(coo_kernel<false, true>, 256)), 256, 0, s>>>(n, nrow, row_ind + e0, nullptr, prod, nullptr, y);
-            THSP_LAUNCH_CHECK();
+            if (launch(n, row_ind + e0, nullptr, prod, true)) return 1;
         }
         return 0;
     }
-    const int want = div_up(div_up(nnz, kCooIPT), 256);   // persistent: see coo_kernel
-    if (vec) coo_kernel<true, false><<<std::min(want, resident_ctas(coo_kernel<true, false>, 256)), 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
-    else coo_kernel<false, false><<<std::min(want, resident_ctas(coo_kernel<false, false>, 256)), 256, 0, s>>>(nnz, nrow, row_ind, col_ind, val, x, y);
-    THSP_LAUNCH_CHECK();
-    return 0;
+    return launch(nnz, row_ind, col_ind, val, false);
 }
 
 int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int* row_ind, const double* val,
@@ -585,9 +657,13 @@ int thsp_csc_spmv_f64(int nrow, int ncol, int nnz, const int* col_ptr, const int
     csc_partition_kernel<<<div_up(nchunks + 1, 256), 256, 0, s>>>(ncol, nnz, col_ptr, nchunks, part);
     THSP_LAUNCH_CHECK();
     const bool vec = ((((uintptr_t)row_ind) | ((uintptr_t)val)) & 31) == 0;   // 256-bit loads of whole sectors
-    // persistent: a CTA keeps its low-row window across its chunks
-    if (vec) csc_kernel<true><<<std::min(nchunks, resident_ctas(csc_kernel<true>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
-    else csc_kernel<false><<<std::min(nchunks, resident_ctas(csc_kernel<false>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    if (csc_head_heavy(nrow, nnz, row_ind, s)) {   // persistent: a CTA keeps its head-row window across its chunks
+        if (vec) csc_kernel<true, true><<<std::min(nchunks, resident_ctas(csc_kernel<true, true>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+        else csc_kernel<false, true><<<std::min(nchunks, resident_ctas(csc_kernel<false, true>, 256)), 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    } else {
+        if (vec) csc_kernel<true, false><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+        else csc_kernel<false, false><<<nchunks, 256, 0, s>>>(nrow, ncol, nnz, col_ptr, row_ind, val, x, y, part, nchunks);
+    }
     THSP_LAUNCH_CHECK();
     return 0;
 }

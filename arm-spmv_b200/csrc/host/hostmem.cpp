@@ -316,14 +316,14 @@ static double trace_origin()
 }
 Trace::Trace(const char* what) : what_(what), t0_(0.0)
 {
-    if (trace_on()) {
+    if (what_ && trace_on()) {
         trace_origin();
         t0_ = now_ms();
     }
 }
 Trace::~Trace()
 {
-    if (trace_on()) fprintf(stderr, "[thsp] at %9.1f ms  %-28s %10.3f ms\n", t0_ - trace_origin(), what_, now_ms() - t0_);
+    if (what_ && trace_on()) fprintf(stderr, "[thsp] at %9.1f ms  %-28s %10.3f ms\n", t0_ - trace_origin(), what_, now_ms() - t0_);
 }
 
 }  // namespace thsp_host

@@ -26,8 +26,19 @@ using namespace thsp_host;
 // Matrix arrays: library-owned (managed) memory is used in place; arrays adopted from the caller
 // (src/matrix.cpp:12-15,88-91) get a device mirror that is uploaded once and found again on later calls
 // (hostmem.h mirror()).  x and y change between calls: host vectors are staged through pooled device buffers.
+namespace {
+struct FirstCalls {   // THSP_TRACE=1: the first three calls of a product are timed (one-time costs against the steady state)
+    int n = 0;
+    bool more() { return n++ < 3; }
+};
+}  // namespace
+#define TRACE_FIRST(name)            \
+    static FirstCalls calls_;        \
+    Trace tr_(calls_.more() ? name : nullptr)
+
 void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y)
 {
+    TRACE_FIRST("COOMatirxMatVector");
     if (A.nnz <= 0) return;
     const int* ri = mirror(A.row_ind, A.nnz);
     const int* ci = mirror(A.col_ind, A.nnz);
@@ -45,6 +56,7 @@ void COOMatirxMatVector(const COOMatrix& A, const Vector& x, Vector& y)
 
 void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y)
 {
+    TRACE_FIRST("CSRMatrixMatVector");
     if (A.nrow <= 0) return;
     View<double> xv(x.values, A.ncol, false), yv(y.values, A.nrow, true);
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -83,6 +95,7 @@ void CSRMatrixMatVector(const CSRMatrix& A, const Vector& x, Vector& y)
 
 void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y)
 {
+    TRACE_FIRST("CSCMatrixMatVector");
     if (A.ncol <= 0) return;
     const int* cp = mirror(A.col_ptr, (size_t)A.ncol + 1);
     const int nnz = cp == A.col_ptr ? peek_int(A.col_ptr + A.ncol) : A.col_ptr[A.ncol];
@@ -101,6 +114,7 @@ void CSCMatrixMatVector(const CSCMatrix& A, const Vector& x, Vector& y)
 
 void ELLMatrixMatVector(const ELLMatrix& A, const Vector& x, Vector& y)
 {
+    TRACE_FIRST("ELLMatrixMatVector");
     const size_t total = (size_t)A.nrow * (size_t)A.nonzeros_in_row;
     if (total == 0) return;
     const int* ci = mirror(A.col_ind, total);
@@ -117,6 +131,7 @@ void ELLMatrixMatVector(const ELLMatrix& A, const Vector& x, Vector& y)
 
 void DIAMatrixMatVector(const DIAMatrix& A, const Vector& x, Vector& y)
 {
+    TRACE_FIRST("DIAMatrixMatVector");
     const size_t total = (size_t)A.nrow * (size_t)A.ndiags;
     if (total == 0) return;
     const int* off = mirror(A.offsets, (size_t)A.ndiags);
