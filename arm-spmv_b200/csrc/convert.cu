@@ -25,7 +25,8 @@
 
 namespace thsp {
 
-void warm_stale_page();   // csr_spmv.cu
+void warm_stale_page();       // csr_spmv.cu
+void warm_format_kernels();   // formats_spmv.cu
 
 // =========================================================== exclusive scan (int32) =======
 static constexpr int kScanThreads = 256;
@@ -1075,6 +1076,7 @@ int thsp_prepare_conversions(int nrow, int ncol, int nnz, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
     warm_stale_page();
+    warm_format_kernels();
     cudaStream_t s = as_stream(stream);
     const int nb = div_up(std::max(nnz, 1), kScanTile);
     if (!scratch(sizeof(int) * 4, 1)) return 1;

@@ -105,51 +105,67 @@ __global__ void __launch_bounds__(256) color_resolve_kernel(int nrow, const int*
         if (unew != vnew) atomicOr(forbid + (unew ? u : v), 1ull << cv);
     }
 }
-// ---- first attempt: the greedy colouring in NATURAL row order, as a fixed-point iteration --------------------------------
-// colour(v) = smallest colour no lower-numbered neighbour has.  That rule has exactly one solution (row 0 first, then
-// row 1, ...), which is what a serial greedy pass would produce, and chaotic iteration reaches it: a row is right as soon
-// as its lower neighbours are.  A row recomputes only when a lower neighbour changed in the previous round (`dirty`), so
-// the work is a wave that crosses the matrix once.  Why bother: on matrices from regular grids this is the parity
-// colouring - 8 colours for a 27-point stencil where the hash-ordered colouring below needs 19 - and the rows of a colour
-// are every other grid point, so that the rows of a 32-row tile of the permuted matrix still gather from x lines they
-// share (profiles/r02_solvers.txt: the sweep went from 6.2 to ... ms).  Deep dependency chains (a tridiagonal matrix needs
-// as many rounds as it has rows) stop at a round limit; what is then inconsistent is repaired by the rounds below.
-__global__ void __launch_bounds__(256) color_natural_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
-                                                            int* color, unsigned* dirty_in, unsigned char* __restrict__ dirty_out,
-                                                            int* __restrict__ counters, int slot)
+// ---- first attempt: the greedy colouring in NATURAL row order, level by level ------------------------------------------
+// colour(v) = smallest colour no lower-numbered neighbour has - what a serial greedy pass over rows 0, 1, 2, ... produces.
+// A row can be coloured as soon as all its lower neighbours are: every row counts its lower neighbours (`pending`), rows
+// with none form the first worklist; a kernel colours the rows of the current worklist and, for each higher neighbour,
+// counts one lower neighbour off - whoever reaches zero goes onto the next worklist.  Every entry is touched twice in
+// all, one small launch per level of the dependency graph (7 n levels on an n^3 27-point stencil).
+// Why bother: on matrices from regular grids this is the parity colouring - 8 colours for a 27-point stencil where the
+// hash-ordered colouring below needs 19 - and the rows of a colour are every other grid point, so that the rows of a
+// 32-row tile of the permuted matrix still gather from x lines they share (profiles/r02_solvers.txt: the sweep went from
+// 6.2 to 2.4 ms).  The first version of this iterated the rule as a fixed point over ALL rows until nothing changed:
+// the same colouring, but rows keep changing until the wave reaches them - 761 rounds x 0.7 ms = 0.53 s on 256^3.
+// Deep graphs (a tridiagonal matrix has as many levels as rows) stop at a level limit; rows never reached - that, or
+// neighbour counts that do not match from both sides in a non-symmetric pattern - stay uncoloured and are finished by the
+// hash-ordered rounds below.
+__global__ void __launch_bounds__(256) level_init_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci,
+                                                         int* __restrict__ color, int* __restrict__ pending, int* __restrict__ list,
+                                                         int* __restrict__ count)
 {
-    // four rows per thread: one 32-bit load tells whether any of them has work (most rounds: none of them)
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    int changed = 0;
-    const unsigned w = 4 * t < nrow ? dirty_in[t] : 0u;
-    if (w) {
-        dirty_in[t] = 0u;   // this buffer is the OUTPUT of the round after next: leave it clean
-        for (int b = 0; b < 4; ++b) {
-            const int v = 4 * t + b;
-            if (!((w >> (8 * b)) & 0xffu) || v >= nrow) continue;
-            unsigned long long used = 0ull;
-            const int e0 = rp[v], e1 = rp[v + 1];
-            for (int p = e0; p < e1; ++p) {
-                const int u = ci[p];
-                if (u >= 0 && u < v) used |= 1ull << color[u];
-            }
-            int c = __ffsll((long long)~used) - 1;
-            if (c < 0) {
-                counters[1] = 1;   // more than 64 colours: give this attempt up
-                c = 63;
-            }
-            if (c != color[v]) {
-                color[v] = c;
-                changed = 1;
-                for (int p = e0; p < e1; ++p) {
-                    const int x = ci[p];
-                    if (x > v && x < nrow) dirty_out[x] = 1;
-                }
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v >= nrow) return;
+    int lower = 0;
+    for (int p = rp[v]; p < rp[v + 1]; ++p) {
+        const int u = ci[p];
+        lower += (u >= 0 && u < v);
+    }
+    color[v] = -1;
+    pending[v] = lower;
+    if (lower == 0) list[atomicAdd(count, 1)] = v;
+}
+__global__ void __launch_bounds__(256) level_round_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ ci, int* color,
+                                                          int* __restrict__ pending, const int* __restrict__ list_in,
+                                                          int* __restrict__ list_out, int* __restrict__ counts, int round,
+                                                          int* __restrict__ overflow)
+{
+    // counts[round % 3] rows wait in list_in; newcomers go to list_out / counts[(round + 1) % 3]; the third counter
+    // (the previous round's input) is reset here for the round after next
+    const int n_in = counts[round % 3];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[(round + 2) % 3] = 0;
+    int* n_out = counts + (round + 1) % 3;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_in; i += gridDim.x * 256) {
+        const int v = list_in[i];
+        unsigned long long used = 0ull;
+        const int e0 = rp[v], e1 = rp[v + 1];
+        for (int p = e0; p < e1; ++p) {
+            const int u = ci[p];
+            if (u >= 0 && u < v) {
+                const int cu = color[u];
+                if (cu >= 0) used |= 1ull << cu;
             }
         }
+        int c = __ffsll((long long)~used) - 1;
+        if (c < 0) {
+            *overflow = 1;   // more than 64 colours: give this attempt up
+            c = 63;
+        }
+        color[v] = c;
+        for (int p = e0; p < e1; ++p) {
+            const int w = ci[p];
+            if (w > v && w < nrow && atomicSub(pending + w, 1) == 1) list_out[atomicAdd(n_out, 1)] = w;
+        }
     }
-    const int any = __syncthreads_count(changed);
-    if (threadIdx.x == 0 && any) atomicAdd(counters + 2 + slot, any);
 }
 // after the natural-order attempt: an entry (v, u) whose ends share a colour sends the higher-numbered one back (it is
 // the one that failed to avoid the other: it cannot see it, or the iteration was cut short) and tells it what to avoid
@@ -160,6 +176,7 @@ __global__ void __launch_bounds__(256) color_verify_kernel(int nrow, const int* 
     const int v = blockIdx.x * 256 + threadIdx.x;
     if (v >= nrow) return;
     const int cv = color[v];
+    if (cv < 0) return;
     for (int p = rp[v]; p < rp[v + 1]; ++p) {
         const int u = ci[p];
         if (u == v || u < 0 || u >= nrow || color[u] != cv) continue;
@@ -379,37 +396,39 @@ int thsp_symgs_plan_create(thsp_symgs_plan** out, int nrow, const int* row_ptr, 
     THSP_CUDA(cudaMemsetAsync(redo, 0, sizeof(int) * ((size_t)nrow + 1), s));
     const int grid = div_up(nrow, 256);
     int rc = 0;
-    {   // natural-order greedy as a fixed point (color_natural_kernel); whatever it leaves inconsistent goes back to -1
+    {   // natural-order greedy, level by level (level_round_kernel); what it does not reach stays at -1
         static const int env_cap = getenv("THSP_COLOR_NATURAL_ROUNDS") ? atoi(getenv("THSP_COLOR_NATURAL_ROUNDS")) : -1;
-        const int cap = env_cap >= 0 ? env_cap : 4096;
-        unsigned char* dirty = nullptr;
-        const size_t dbytes = (((size_t)nrow + 3) & ~(size_t)3) + 256;   // each buffer a whole number of 32-bit words
-        int* cnt = nullptr;
-        THSP_CUDA(cudaMalloc(&dirty, 2 * dbytes));
-        THSP_CUDA(cudaMalloc(&cnt, sizeof(int) * 16));
-        THSP_CUDA(cudaMemsetAsync(cin, 0, sizeof(int) * (size_t)nrow, s));
-        THSP_CUDA(cudaMemsetAsync(dirty, 1, dbytes, s));            // round 0: every row computes
-        THSP_CUDA(cudaMemsetAsync(dirty + dbytes, 0, dbytes, s));
-        THSP_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 16, s));
+        const int cap = env_cap >= 0 ? env_cap : 16384;
+        int *pending = nullptr, *lists = nullptr, *cnt = nullptr;
+        THSP_CUDA(cudaMalloc(&pending, sizeof(int) * (size_t)nrow));
+        THSP_CUDA(cudaMalloc(&lists, sizeof(int) * 2 * (size_t)nrow));
+        THSP_CUDA(cudaMalloc(&cnt, sizeof(int) * 8));
+        THSP_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 8, s));
         bool gave_up = cap == 0;
-        const int grid4 = div_up(div_up(nrow, 4), 256);
-        for (int round = 0; round < cap; ++round) {
-            unsigned char* din = dirty + (size_t)(round & 1) * dbytes;
-            unsigned char* dout = dirty + (size_t)((round + 1) & 1) * dbytes;
-            color_natural_kernel<<<grid4, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, reinterpret_cast<unsigned*>(din), dout, cnt, round & 7);
+        if (!gave_up) {
+            level_init_kernel<<<grid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, pending, lists, cnt);
+            THSP_LAUNCH_CHECK();
+        } else {
+            THSP_CUDA(cudaMemsetAsync(cin, 0xff, sizeof(int) * (size_t)nrow, s));
+        }
+        const int lgrid = std::min(grid, sm_count() * 4);
+        for (int round = 0; round < cap && !gave_up; ++round) {
+            int* lin = lists + (size_t)(round & 1) * nrow;
+            int* lout = lists + (size_t)((round + 1) & 1) * nrow;
+            level_round_kernel<<<lgrid, 256, 0, s>>>(nrow, row_ptr, col_ind, cin, pending, lin, lout, cnt, round, cnt + 4);
             THSP_LAUNCH_CHECK();
             p->natural_rounds = round + 1;
-            if ((round & 7) == 7 || round + 1 == cap) {   // look at the counters every eighth round only
-                int h[10];
+            if ((round & 31) == 31 || round + 1 == cap) {   // look at the counters every 32nd level only
+                int h[5];
                 THSP_CUDA(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
-                THSP_CUDA(cudaMemsetAsync(cnt + 2, 0, sizeof(int) * 8, s));
                 THSP_CUDA(cudaStreamSynchronize(s));
-                if (h[1]) { gave_up = true; break; }
-                if (h[2 + (round & 7)] == 0) break;   // the last round changed nothing: nothing is dirty, the fixed point is reached
+                if (h[4]) gave_up = true;
+                if (h[(round + 1) % 3] == 0) break;   // nobody is waiting for the next level
             }
         }
+        cudaFree(pending);
+        cudaFree(lists);
         cudaFree(cnt);
-        cudaFree(dirty);
         if (gave_up) {
             THSP_CUDA(cudaMemsetAsync(cin, 0xff, sizeof(int) * (size_t)nrow, s));
             p->natural_rounds = 0;
