@@ -124,11 +124,15 @@ struct GsEpilogue {
     V* x = nullptr;   // the same vector the kernel gathers from: rows of one colour never read each other's entries
 };
 
-template <typename V, bool kGs>
+// kScale: every gathered x_j is multiplied by *xscale before it meets its matrix entry - y = A (s x) without a pass
+// that writes s x first.  The power iteration keeps its vector unnormalised and hands the SpMV 1/||y|| of the previous
+// step (power.py "deferred" modes): mul_rn(x_j, s) is the very product the normalising pass would have stored, so y has
+// the same bits, and one read and one write of the vector per iteration are gone.
+template <typename V, bool kGs, bool kScale>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
-                      V* __restrict__ tile_ss, int* __restrict__ stale, GsEpilogue<V> gs)
+                      V* __restrict__ tile_ss, int* __restrict__ stale, GsEpilogue<V> gs, const V* __restrict__ xscale)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(768, 1)
     const uint64_t pol = policy_evict_first();
     const int GW = gridDim.x * W;
     const int gw = blockIdx.x * W + warp;
+    V xs = V(1);
+    if (kScale) xs = __ldg(xscale);
 
     // ---- producer cursor (warp-uniform): runs S chunks ahead of the consumer --------------
     int p_tile = gw, p_slot = 0, p_chunk = 0, p_nch = 0, p_al = 0, p_te = 0, p_stage = 0;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(768, 1)
                 for (int u = 0; u < U; ++u) vv[u] = (j + u < hi) ? sv[j + u] : V(0);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (j + u < hi) sum = add_rn(sum, mul_rn(vv[u], xx[u]));  // skipped, not "+0": keeps -0.0 sums exact
+                    if (j + u < hi) sum = add_rn(sum, mul_rn(vv[u], kScale ? mul_rn(xx[u], xs) : xx[u]));  // skipped, not "+0": keeps -0.0 sums exact
             }
         }
         __syncwarp();
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(768, 1)
 template <typename V>
 static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
                       const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, int* stale = nullptr,
-                      GsEpilogue<V> gs = GsEpilogue<V>())
+                      GsEpilogue<V> gs = GsEpilogue<V>(), const V* xscale = nullptr)
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
@@ -317,15 +323,18 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
     THSP_CUDA(cudaGetDevice(&dev));
     size_t& cur = configured[dev & 15][sizeof(V) == 8 ? 0 : 1];
     if (smem > cur) {
-        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cur = 227 * 1024;
     }
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    if (gs.rows) csr_stream_kernel<V, true><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs);
-    else csr_stream_kernel<V, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs);
+    THSP_REQUIRE(!(gs.rows && xscale), "the Gauss-Seidel epilogue and a scaled x are not combined");
+    if (gs.rows) csr_stream_kernel<V, true, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr);
+    else if (xscale) csr_stream_kernel<V, false, true><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, xscale);
+    else csr_stream_kernel<V, false, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr);
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -868,14 +877,15 @@ static void choose_stateless(int nrow, int nnz, const void* val, const int* col,
 }
 
 template <typename V>
-static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr)
+static int plan_spmv(const thsp_csr_plan* p, const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, const V* xscale = nullptr)
 {
     if (p->nrow <= 0) return 0;
+    THSP_REQUIRE(!xscale || p->kernel == THSP_CSR_STREAM, "a scaled x is folded into the stream kernel only");
     if (p->kernel == THSP_CSR_MERGE)
         return run_merge<V>(p->nrow, p->nnz, p->row_ptr, p->col_ind, static_cast<const V*>(p->val), x, y, acc, nullptr, s, p->stale);
     if (p->kernel == THSP_CSR_STREAM)
         return run_stream<V>(p->stream_cfg, p->ctas, p->nrow, p->nnz, p->row_ptr, p->col_ind,
-                             static_cast<const V*>(p->val), x, y, acc, s, tile_ss, p->stale);
+                             static_cast<const V*>(p->val), x, y, acc, s, tile_ss, p->stale, GsEpilogue<V>(), xscale);
     return dispatch<V>(p->kernel, p->lanes, &p->stream_cfg, p->nrow, p->ncol, p->nnz, p->row_ptr, p->col_ind,
                        static_cast<const V*>(p->val), x, y, acc, s);
 }
@@ -1092,6 +1102,14 @@ int thsp_csr_plan_spmv_sumsq_f64(const thsp_csr_plan* plan, const double* x, dou
     if (plan->kernel == THSP_CSR_STREAM) return plan_spmv<double>(plan, x, y, accumulate, as_stream(stream), tile_ss);
     if (plan_spmv<double>(plan, x, y, accumulate, as_stream(stream))) return 1;
     return thsp_tile_sumsq_f64(plan->nrow, y, tile_ss, stream);   // the same numbers from a pass over y
+}
+int thsp_csr_plan_spmv_scaled_f64(const thsp_csr_plan* plan, const double* x, const double* xscale, double* y, int accumulate,
+                                  double* tile_ss, thsp_stream_t stream)
+{
+    THSP_REQUIRE(plan != nullptr && plan->value_bytes == 8, "plan is null or not fp64");
+    THSP_REQUIRE(xscale != nullptr, "xscale is the device scalar every x_j is multiplied by");
+    THSP_REQUIRE(plan->kernel == THSP_CSR_STREAM, "thsp_csr_plan_spmv_scaled_f64 needs a plan that runs the stream kernel");
+    return plan_spmv<double>(plan, x, y, accumulate, as_stream(stream), tile_ss, xscale);
 }
 int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, float* y, int accumulate, thsp_stream_t stream)
 {

@@ -281,6 +281,106 @@ __global__ void __launch_bounds__(kXThreads) xchg_norm_scale_push_kernel(int nti
     }
 }
 
+// ---- the same step with the normalisation DEFERRED into the next product ---------------------------------------------
+// x = y / ||y|| is never written: the next SpMV multiplies every gathered y_j by 1/||y|| itself (csr_stream_kernel,
+// kScale - the same rounding the normalising pass would have done, so y keeps its bits).  What is left of the vector half:
+//   1. the tree over the tile partials, published to every rank (as above);
+//   2. the pieces of the RAW y that other ranks read, copied into their replicas of the vector (16-byte stores over
+//      NVLink where the piece is aligned), then the "pieces from <rank>" flags - none of this waits for the norm;
+//   3. the CTA that published waits for the partials of all ranks, combines them (tree over rank numbers) and leaves the
+//      sum and 1/sqrt(sum) on the device for the next product.
+// Nothing here reads or writes the n-element vector except the pushed pieces: the 2 x 8 n bytes of the normalising pass
+// are gone, and only one CTA waits for the peers (no cooperative launch).
+__global__ void __launch_bounds__(kXThreads) xchg_norm_push_kernel(int ntiles, const double* __restrict__ tile_ss, double* part,
+                                                                   unsigned* __restrict__ tickets, const double* __restrict__ y,
+                                                                   uint64_t iter, int world, int rank, XPeers peers, int64_t offset,
+                                                                   XDests dst, double* __restrict__ sumsq_out, double* __restrict__ inv_out)
+{
+    __shared__ bool last_tree, last_push;
+    static_assert(kXThreads == kTreeThreads, "block_tree_sum is written for this CTA size");
+    const int nb = (ntiles + kTreeBlock - 1) / kTreeBlock;
+    double* part_b = part + nb;
+    const int par = (int)(iter & 1);
+    // ---- 1. this rank's partial
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const double r = block_tree_sum(tile_ss + (size_t)b * kTreeBlock, min(kTreeBlock, ntiles - b * kTreeBlock));
+        if (threadIdx.x == 0) part[b] = r;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last_tree = atomicAdd(tickets, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_tree) {
+        __threadfence();
+        const double mine = nb > 0 ? block_tree_finish(part, nb, part, part_b) : 0.0;
+        if (threadIdx.x < 32) {
+            const int p = threadIdx.x;
+            if (p == 0) tickets[0] = 0;
+            if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPart + par * kXMaxRanks + rank, (uint64_t)__double_as_longlong(mine));
+            __threadfence_system();
+            if (p < world) st_relaxed_sys(peers.ctrl[p] + kXPartFlag + par * kXMaxRanks + rank, iter);
+        }
+    }
+    // ---- 2. the pieces of y the neighbours read, as they are
+    if (dst.n > 0) {
+        bool remote = false;
+        const int64_t t = (int64_t)blockIdx.x * kXThreads + threadIdx.x, stride = (int64_t)gridDim.x * kXThreads;
+        for (int d = 0; d < dst.n; ++d) {
+            const int64_t lo = dst.lo[d], len = dst.hi[d] - dst.lo[d];
+            if (len <= 0) continue;
+            const double* src = y + (lo - offset);
+            double* out = dst.x[d] + lo;
+            if (((((uintptr_t)src) | ((uintptr_t)out)) & 15) == 0) {
+                const int64_t n2 = len >> 1;
+                for (int64_t i = t; i < n2; i += stride) {
+                    reinterpret_cast<double2*>(out)[i] = ld_stream2(src + 2 * i);
+                    remote = true;
+                }
+                if ((len & 1) && t == 0) {
+                    out[len - 1] = src[len - 1];
+                    remote = true;
+                }
+            } else {
+                for (int64_t i = t; i < len; i += stride) {
+                    out[i] = ld_stream(src + i);
+                    remote = true;
+                }
+            }
+        }
+        if (remote) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last_push = atomicAdd(tickets + 1, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last_push && threadIdx.x < 32) {
+            if (threadIdx.x == 0) tickets[1] = 0;
+            __threadfence_system();
+            if ((int)threadIdx.x < dst.n) st_relaxed_sys(dst.ctrl[threadIdx.x] + kXHalo + rank, iter);
+        }
+    }
+    // ---- 3. everybody's partials, combined by the tree over rank numbers: the norm for the next product
+    if (last_tree && threadIdx.x < 32) {
+        uint64_t* ctrl = peers.ctrl[rank];
+        const int r = threadIdx.x;
+        double v = 0.0;
+        bool ok = true;
+        if (r < world) {
+            ok = spin_until(ctrl + kXPartFlag + par * kXMaxRanks + r, iter, ctrl + kXErr);
+            v = __longlong_as_double((long long)ld_acquire_sys(ctrl + kXPart + par * kXMaxRanks + r));
+        }
+#pragma unroll
+        for (int o = 1; o < kXMaxRanks; o <<= 1) v = add_rn(v, __shfl_down_sync(0xffffffffu, v, o));   // lanes >= world hold +0.0
+        if (!__all_sync(0xffffffffu, ok)) v = __longlong_as_double(0x7ff8000000000000LL);   // a peer never showed up: loud
+        if (r == 0) {
+            *sumsq_out = v;
+            *inv_out = __ddiv_rn(1.0, __dsqrt_rn(v));
+        }
+    }
+}
+
 __global__ void xchg_wait_kernel(uint64_t* ctrl, uint64_t iter, unsigned src_mask)
 {
     if (threadIdx.x != 0) return;
@@ -378,6 +478,45 @@ int thsp_xchg_norm_scale_push_f64(int64_t n, const double* y, const double* tile
     double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
     void* args[] = {&ntiles, (void*)&tile_ss, &part, &tickets, &n, (void*)&y, &iter, &world, &rank, &pe, &x_local, &offset, &d, &sumsq_out};
     THSP_CUDA(cudaLaunchCooperativeKernel((const void*)xchg_norm_scale_push_kernel, dim3(grid), dim3(kXThreads), args, 0, as_stream(stream)));
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+int thsp_xchg_norm_push_f64(int64_t n, const double* y, const double* tile_ss, uint64_t iter, int world, int rank,
+                            void* const* peer_ctrl, void* work, int64_t offset, int ndest, double* const* dest_x,
+                            void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi, double* sumsq_out,
+                            double* inv_out, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    THSP_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, "bad world / rank");
+    THSP_REQUIRE(ndest >= 0 && ndest < kXMaxRanks, "too many destinations");
+    THSP_REQUIRE(sumsq_out != nullptr && inv_out != nullptr && tile_ss != nullptr, "tile_ss / sumsq_out / inv_out missing");
+    const int64_t ntiles64 = (n + 31) / 32;
+    THSP_REQUIRE(ntiles64 <= (int64_t)4095 * kTreeBlock, "slice too long for the work buffer");
+    XPeers pe;
+    for (int p = 0; p < kXMaxRanks; ++p) pe.ctrl[p] = p < world ? static_cast<uint64_t*>(peer_ctrl[p]) : nullptr;
+    XDests d;
+    d.n = ndest;
+    int64_t pushed = 0;
+    for (int k = 0; k < kXMaxRanks; ++k) {
+        d.x[k] = k < ndest ? dest_x[k] : nullptr;
+        d.ctrl[k] = k < ndest ? static_cast<uint64_t*>(dest_ctrl[k]) : nullptr;
+        d.lo[k] = k < ndest ? dest_lo[k] : 0;
+        d.hi[k] = k < ndest ? dest_hi[k] : 0;
+        if (k < ndest) {
+            THSP_REQUIRE(dest_lo[k] >= offset && dest_hi[k] <= offset + n, "a rank pushes pieces of its own slice only");
+            pushed = std::max(pushed, dest_hi[k] - dest_lo[k]);
+        }
+    }
+    int ntiles = (int)ntiles64;
+    const int nb = (ntiles + kTreeBlock - 1) / kTreeBlock;
+    // enough CTAs for the blocks of the tree and for 16-byte stores of the longest piece, at most two per SM
+    const int64_t want = std::max<int64_t>(nb, (pushed / 2 + kXThreads - 1) / kXThreads);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 2));
+    unsigned* tickets = static_cast<unsigned*>(work);
+    double* part = reinterpret_cast<double*>(static_cast<char*>(work) + 64);
+    xchg_norm_push_kernel<<<grid, kXThreads, 0, as_stream(stream)>>>(ntiles, tile_ss, part, tickets, y, iter, world, rank, pe, offset, d,
+                                                                    sumsq_out, inv_out);
     THSP_LAUNCH_CHECK();
     return 0;
 }

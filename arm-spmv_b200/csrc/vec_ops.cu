@@ -258,6 +258,19 @@ int thsp_tree_sum_f64(int64_t m, const double* vals, double* out_dev, thsp_strea
     return 0;
 }
 
+// out[i] = x[i] * *scale (what the stream kernel's scaled-x variant does on the fly, as a pass: for plans that run
+// another kernel)
+int thsp_scale_by_dev_f64(int64_t n, const double* x, const double* scale_dev, double* out, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { out[i] = mul_rn(x[i], __ldg(scale_dev)); });
+}
+// *inv = 1 / sqrt(*sumsq): the factor of vec_axpby(1/sqrt(s), y, 0, y), left on the device for the next product
+int thsp_inv_sqrt_dev_f64(const double* sumsq_dev, double* inv_dev, thsp_stream_t stream)
+{
+    if (ensure_device()) return 1;
+    return launch_ew(1, as_stream(stream), [=] __device__(int64_t) { *inv_dev = __ddiv_rn(1.0, __dsqrt_rn(*sumsq_dev)); });
+}
 int thsp_axpby_f64(int64_t n, double alpha, const double* x, double beta, const double* y, double* w, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;

@@ -131,9 +131,20 @@ class CudaOps:
         self.check(self.lib.thsp_csc_spmv_f64(payload.nrow, payload.ncol, payload.nnz, self.ptr(payload.col_ptr), self.ptr(payload.row_ind),
                                               self.ptr(payload.values), self.ptr(x), self.ptr(y), self.stream()))
 
-    def spmv(self, payload, x, y, tile_ss=None):
+    def spmv(self, payload, x, y, tile_ss=None, xscale=None):
         """y = A_block x (overwrite: saves Fill(0) and the read of y); with tile_ss also the sum of squares of every
-        32-row tile of y, written by the SpMV's epilogue (thsp_csr_plan_spmv_sumsq_f64)."""
+        32-row tile of y, written by the SpMV's epilogue (thsp_csr_plan_spmv_sumsq_f64); with xscale (device scalar)
+        y = A_block (xscale * x), the factor applied to every gathered x_j inside the stream kernel."""
+        if xscale is not None:
+            if payload.plan_kernel()[0] == "stream":
+                self.check(self.lib.thsp_csr_plan_spmv_scaled_f64(payload.plan(), self.ptr(x), self.ptr(xscale), self.ptr(y), 0,
+                                                                  self.ptr(tile_ss), self.stream()))
+                return
+            # other kernels (short or irregular rows): the same products from a scaled copy of x
+            if getattr(self, "_xs", None) is None or self._xs.numel() != x.numel():
+                self._xs = self.empty(x.numel())
+            self.check(self.lib.thsp_scale_by_dev_f64(C.c_int64(x.numel()), self.ptr(x), self.ptr(xscale), self.ptr(self._xs), self.stream()))
+            x = self._xs
         if tile_ss is None:
             self.check(self.lib.thsp_csr_plan_spmv_f64(payload.plan(), self.ptr(x), self.ptr(y), 0, self.stream()))
         else:
@@ -142,6 +153,16 @@ class CudaOps:
     def tree_sum(self, vals, out):
         """out[0] = the canonical (index-bit tree) sum of vals: tile partials of one rank, or the ranks' partials."""
         self.check(self.lib.thsp_tree_sum_f64(C.c_int64(vals.numel()), self.ptr(vals), self.ptr(out), self.stream()))
+
+    def inv_sqrt(self, ss, inv):
+        """inv[0] = 1 / sqrt(ss[0]), on the device"""
+        self.check(self.lib.thsp_inv_sqrt_dev_f64(self.ptr(ss), self.ptr(inv), self.stream()))
+
+    def scaled(self, x, scale):
+        """a new vector scale[0] * x (what a deferred normalisation would have stored)"""
+        out = self.empty(x.numel())
+        self.check(self.lib.thsp_scale_by_dev_f64(C.c_int64(x.numel()), self.ptr(x), self.ptr(scale), self.ptr(out), self.stream()))
+        return out
 
     def hash(self, v, first):
         h = C.c_uint64(0)
@@ -194,6 +215,19 @@ class CudaOps:
         self.d_ctrl = (C.c_void_p * max(n, 1))(*[self.ctrl_ptrs[r] for r, _, _ in dests])
         self.d_lo = (C.c_int64 * max(n, 1))(*[lo for _, lo, _ in dests])
         self.d_hi = (C.c_int64 * max(n, 1))(*[hi for _, _, hi in dests])
+
+    def xchg_dests2(self, dests, peer_ptr_sets):
+        """the same pieces for each of the two vectors of the deferred loop (DeferredPowerIteration)"""
+        self.xchg_dests(dests, peer_ptr_sets[0])
+        n = len(dests)
+        self.d_x2 = [(C.c_void_p * max(n, 1))(*[ptrs[r] for r, _, _ in dests]) for ptrs in peer_ptr_sets]
+
+    def norm_push(self, y, tile_ss, it, xout, offset, ss, inv, which):
+        """tree + publish + push of the raw pieces + flags + combine -> ss, inv (thsp_xchg_norm_push_f64); `which` = the
+        vector (0 / 1) the pieces belong to on every rank; xout is this rank's copy of it (the kernel goes by pointers)"""
+        self.check(self.lib.thsp_xchg_norm_push_f64(C.c_int64(y.numel()), self.ptr(y), self.ptr(tile_ss), C.c_uint64(it), self.xw, self.xr,
+                                                    self.ctrl_arr, self.ptr(self.work), C.c_int64(offset), self.nd, self.d_x2[which],
+                                                    self.d_ctrl, self.d_lo, self.d_hi, self.ptr(ss), self.ptr(inv), self.stream()))
 
     def sumsq_publish(self, y, it):
         self.check(self.lib.thsp_xchg_sumsq_publish_f64(C.c_int64(y.numel()), self.ptr(y), C.c_uint64(it), self.xw, self.xr, self.ctrl_arr,
@@ -261,15 +295,16 @@ class PartitionedCSR:
         bnd = world > 1 and (lo < start or hi >= start + count)
         return PartitionedCSR(nrow, rank, world, start, count, [RowBlock(start, count, nnz, bnd, payload, lo, hi)])
 
-    def spmv(self, ops, x, y_local, boundary: bool | None = None, tile_ss=None):
+    def spmv(self, ops, x, y_local, boundary: bool | None = None, tile_ss=None, xscale=None):
+        kw = {} if xscale is None else {"xscale": xscale}
         for b in self.blocks:
             if boundary is None or b.boundary == boundary:
                 off = b.row0 - self.start
                 if tile_ss is None:
-                    ops.spmv(b.payload, x, y_local[off:off + b.nrow])
+                    ops.spmv(b.payload, x, y_local[off:off + b.nrow], **kw)
                 else:   # blocks start on tile boundaries of the slice (stencil_row_blocks, from_csr)
                     assert off % 32 == 0
-                    ops.spmv(b.payload, x, y_local[off:off + b.nrow], tile_ss[off // 32:off // 32 + (b.nrow + 31) // 32])
+                    ops.spmv(b.payload, x, y_local[off:off + b.nrow], tile_ss[off // 32:off // 32 + (b.nrow + 31) // 32], **kw)
 
     def needed_ranges(self) -> list[tuple[int, int, int]]:
         """(owner rank, lo, hi) pieces of x outside the own slice that the boundary blocks read."""
@@ -517,6 +552,132 @@ class PowerIteration:
         return a.nnz_local * 12 + (rows + len(a.blocks)) * 4 + x_read * 8 + rows * 8 + rows * 16
 
 
+class DeferredPowerIteration:
+    """The same loop with the normalisation deferred into the next product.  x = y / ||y|| is never stored: the vector
+    stays as the SpMV left it and the next SpMV multiplies every gathered y_j by 1/||y|| on the fly
+    (thsp_csr_plan_spmv_scaled_f64) - the product mul_rn(y_j, 1/||y||) is the very number the normalising pass would
+    have written, so y and ||y|| have the same bits as in PowerIteration, step by step, on any number of GPUs, while one
+    read and one write of the vector per iteration are gone.  Two vectors alternate (a product cannot overwrite what it
+    gathers from); a rank's rows of y ARE its slice of the next input.  exchange: "deferred" on one GPU; "xchgd" across
+    GPUs = the flag-based exchange of `xchg` moving the RAW pieces (thsp_xchg_norm_push_f64: nothing in the vector half
+    waits for the norm except the scalar itself).  `x` materialises the normalised vector on demand."""
+    deferred = True
+
+    def __init__(self, A: PartitionedCSR, ops, exchange: str = "xchgd", overlap: bool = True, group=None, seed: int = 11,
+                 reserve_sms: int = 16):
+        self.A, self.ops, self.exchange, self.overlap, self.group = A, ops, exchange, overlap, group
+        self.world, self.rank = A.world, A.rank
+        if hasattr(ops, "reserve_sms"):
+            for b in A.blocks:
+                ops.reserve_sms(b.payload, 0)
+        self.ss, self.inv = ops.scalar(), ops.scalar()
+        self.inv.fill_(1.0)   # x0 is taken as it is: multiplying by 1.0 changes no bit
+        self.tile_ss = ops.empty((A.count + 31) // 32)
+        self.symm = []
+        if self.world > 1 and hasattr(ops, "symmetric_x"):
+            self.buf = [ops.symmetric_x(A.N), ops.symmetric_x(A.N)]     # CPU test ops: plain memory, pushes emulated over gloo
+            peer_sets = [None, None]
+        elif self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            name = dist.group.WORLD.group_name if group is None else group.group_name
+            self.buf, peer_sets = [], []
+            for _ in range(2):
+                t = symm_mem.empty(A.N, dtype=torch.float64, device=ops.device)
+                h = symm_mem.rendezvous(t, group=name)
+                self.buf.append(t)
+                self.symm.append(h)
+                peer_sets.append([int(h.buffer_ptrs[r]) for r in range(self.world)])
+        else:
+            self.buf = [ops.empty(A.N), ops.empty(A.N)]
+        self.cur = 0     # the vector the next product reads
+        self.iter = 0
+        self.trace = None
+        self.src_mask = 0
+        if self.world > 1:
+            pg = dist.group.WORLD if group is None else group
+            ops.xchg_setup(self.world, self.rank, getattr(pg, "group_name", ""))
+            needs = A.needed_ranges()
+            all_needs = [None] * self.world
+            dist.all_gather_object(all_needs, needs, group=group)
+            ops.xchg_dests2(pushes_from_needs(all_needs, self.rank), peer_sets)
+            for owner, _, _ in needs:
+                self.src_mask |= 1 << owner
+        if hasattr(ops, "init_x"):
+            ops.init_x(self.buf[0], seed)
+        else:
+            ops.check(ops.lib.thsp_gen_vector_f64(C.c_int64(A.N), C.c_uint64(seed), ops.ptr(self.buf[0]), ops.stream()))
+        if self.symm:
+            torch.cuda.synchronize()
+            self.symm[0].barrier()
+
+    # the phase trace of PowerIteration
+    trace_on = PowerIteration.trace_on
+    _mark = PowerIteration._mark
+    trace_report = PowerIteration.trace_report
+
+    @property
+    def y(self):
+        """this rank's rows of the last product (they sit in the vector the next product reads)"""
+        return self.buf[self.cur][self.A.start:self.A.start + self.A.count]
+
+    @property
+    def x(self):
+        """the normalised vector y / ||y|| (x0 before the first step): own slice and the pieces this rank reads"""
+        return self.ops.scaled(self.buf[self.cur], self.inv)
+
+    def step(self):
+        A, ops = self.A, self.ops
+        k = self.iter + 1
+        xin, xout = self.buf[self.cur], self.buf[1 - self.cur]
+        yown = xout[A.start:A.start + A.count]
+        self._mark("start")
+        if self.world > 1 and self.overlap:
+            A.spmv(ops, xin, yown, boundary=False, tile_ss=self.tile_ss, xscale=self.inv)
+            self._mark("interior rows")
+            ops.wait_halo(k - 1, self.src_mask)
+            self._mark("wait for neighbours")
+            A.spmv(ops, xin, yown, boundary=True, tile_ss=self.tile_ss, xscale=self.inv)
+            self._mark("boundary rows")
+        else:
+            if self.world > 1:
+                ops.wait_halo(k - 1, self.src_mask)
+            A.spmv(ops, xin, yown, tile_ss=self.tile_ss, xscale=self.inv)
+            self._mark("all rows")
+        if self.world > 1:
+            ops.norm_push(yown, self.tile_ss, k, xout, A.start, self.ss, self.inv, 1 - self.cur)
+            self._mark("tree + publish + push + combine")
+        else:
+            ops.tree_sum(self.tile_ss, self.ss)
+            ops.inv_sqrt(self.ss, self.inv)
+            self._mark("sum of squares + 1/sqrt")
+        self.cur = 1 - self.cur
+        self.iter = k
+
+    def norm(self) -> float:
+        if self.world > 1 and hasattr(self.ops, "xchg_timed_out") and self.ops.xchg_timed_out():
+            raise RuntimeError("flag-based exchange: a wait on a peer gave up (peer stalled or died)")
+        return math.sqrt(float(self.ss.item()))
+
+    def y_hash(self) -> int:
+        return self.ops.hash(self.y, self.A.start)
+
+    def bytes_per_step(self) -> int:
+        """CSR stream + the columns read once + y written; no normalising pass"""
+        a = self.A
+        lo = min((b.col_min for b in a.blocks), default=0)
+        hi = max((b.col_max for b in a.blocks), default=-1)
+        return a.nnz_local * 12 + (a.count + len(a.blocks)) * 4 + max(0, hi - lo + 1) * 8 + a.count * 8
+
+
+DEFERRED_MODES = ("deferred", "xchgd")
+
+
+def make_iteration(A, ops, exchange="allgather", **kw):
+    """PowerIteration, or DeferredPowerIteration for the modes that fold the normalisation into the next product."""
+    cls = DeferredPowerIteration if exchange in DEFERRED_MODES else PowerIteration
+    return cls(A, ops, exchange=exchange, **kw)
+
+
 def _all_gather_slices(x, own, n, world, equal_split, group):
     """Every rank's slice into every replica of x.  Equal slices: one in-place all-gather.  The
     reference's rule gives the last block the remainder (src/mat_vec.cpp:245-246); collectives
@@ -672,7 +833,7 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
     sync_token = torch.zeros(1, device=device)
     for mode in modes:
         try:
-            it = PowerIteration(A, ops, exchange=mode, overlap=overlap, reserve_sms=reserve_sms)
+            it = make_iteration(A, ops, exchange=mode, overlap=overlap, reserve_sms=reserve_sms)
         except Exception as e:  # e.g. symmetric memory not available on this box
             results[mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
             continue
@@ -712,7 +873,7 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
             results[mode]["phases_ms"] = {k: round(v, 4) for k, v in rep.items()}
             print(f"[trace rank {rank} {mode}] " + "  ".join(f"{k}: {v:.3f}" for k, v in rep.items()), flush=True)
             it.trace = None
-        if with_e2e and "e2e" not in results:
+        if with_e2e and "e2e" not in results and not getattr(it, "deferred", False):
             xh = torch.empty(A.count, dtype=torch.float64).pin_memory()
             yh = torch.empty(A.count, dtype=torch.float64).pin_memory()
             xh.copy_(it.x[A.start:A.start + A.count].cpu())
@@ -778,6 +939,10 @@ def measure(n, rank, world, device, steps, warmup, modes, overlap, ClockSampler,
 
 
 MODE_NOTES = {
+    "xchgd": "normalisation deferred into the next SpMV (every gathered y_j times 1/||y|| inside the stream kernel: same bits, no "
+             "pass over the vector); the raw pieces the neighbours read and the partial sums of squares go straight into their memory "
+             "over NVLink with flags (thsp_xchg_norm_push_f64); no collective call in the loop",
+    "deferred": "one GPU: normalisation deferred into the next SpMV, no pass over the vector",
     "xchg": "each rank stores the pieces of x its neighbours read, and its partial sum of squares, straight into their memory "
             "over NVLink and raises a flag (csrc/exchange.cu); no collective call in the loop",
     "allgather": "NCCL in-place all-gather of every slice into every replica (BASELINE.json's wording), overlapped with the interior rows",
@@ -811,8 +976,19 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler, extra=None
     if world > 1 and not getattr(args, "no_one_gpu", False):
         if rank == 0:
             try:
-                A1, res1 = measure(n, 0, 1, device, args.steps, args.warmup, ["allgather"], True, ClockSampler, with_e2e=False, hash_parts=world)
-                one = res1["allgather"]
+                A1, res1 = measure(n, 0, 1, device, args.steps, args.warmup, ["deferred", "allgather"], True, ClockSampler, with_e2e=False,
+                                   hash_parts=world)
+                eager, lazy = res1["allgather"], res1.get("deferred", {})
+                # the denominator is the faster one-GPU loop; both must agree bit for bit (same products, same sums)
+                use_lazy = "ms_per_step" in lazy and lazy["ms_per_step"] < eager["ms_per_step"]
+                one = dict(lazy if use_lazy else eager)
+                one["loop"] = "normalisation deferred into the next SpMV" if use_lazy else "SpMV, sum of squares, normalising pass"
+                one["eager_ms_per_step"] = eager["ms_per_step"]
+                if "ms_per_step" in lazy:
+                    one["deferred_ms_per_step"] = lazy["ms_per_step"]
+                    one["deferred_equals_eager_bits"] = bool(lazy["norm"] == eager["norm"] and lazy["y_hash_parts"] == eager["y_hash_parts"])
+                else:
+                    one["deferred"] = lazy
                 one["row_blocks"] = len(A1.blocks)
                 del A1, res1
             except Exception as e:   # e.g. out of memory on a smaller GPU: the line then says so instead of a ratio
@@ -857,8 +1033,11 @@ def bench_main(args, METRIC, UNIT, csr_bytes, peak_hbm, ClockSampler, extra=None
         if one is not None and "ms_per_step" in one:
             ms1 = one["ms_per_step"]
             line["same_workload_1gpu"] = {"ms_per_step": round(ms1, 5), "gflops": round(flops / (ms1 * 1e-3) / 1e9, 2), "norm": one["norm"],
-                                          "steps_done": one["steps_done"], "row_blocks": one["row_blocks"],
-                                          "note": "the same power iteration on rank 0's GPU alone, timed in this run before the ranks start"}
+                                          "steps_done": one["steps_done"], "row_blocks": one["row_blocks"], "loop": one.get("loop"),
+                                          "eager_ms_per_step": round(one["eager_ms_per_step"], 5),
+                                          "deferred_ms_per_step": round(one["deferred_ms_per_step"], 5) if "deferred_ms_per_step" in one else None,
+                                          "deferred_equals_eager_bits": one.get("deferred_equals_eager_bits"),
+                                          "note": "the same power iteration on rank 0's GPU alone (the faster of its two forms), timed in this run before the ranks start"}
             line["speedup_vs_1gpu_same_workload"] = round(ms1 / ms, 4)
             line["efficiency_same_workload"] = round(ms1 / ms / world, 4)
             for m, v in line["x_refresh_modes"].items():

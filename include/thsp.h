@@ -134,6 +134,12 @@ THSP_API int thsp_csr_plan_spmv_f32(const thsp_csr_plan* plan, const float* x, f
  * read again - the other kernels are followed by thsp_tile_sumsq_f64. */
 THSP_API int thsp_csr_plan_spmv_sumsq_f64(const thsp_csr_plan* plan, const double* x, double* y, int accumulate,
                                           double* tile_ss, thsp_stream_t stream);
+/* y = A (s x) with s = *xscale read from the device when the kernel starts: every gathered x_j is multiplied by s
+ * (one rounding, as a pass x <- s x would have done - same bits of y) before it meets its matrix entry.  Lets an iterated
+ * loop keep its vector unnormalised: x = vec_axpby(1/nrm, y, 0, y) (src/vec_vec.cpp:46-53) is never written.  Needs a
+ * plan that runs the stream kernel (error otherwise); tile_ss as above, or NULL. */
+THSP_API int thsp_csr_plan_spmv_scaled_f64(const thsp_csr_plan* plan, const double* x, const double* xscale, double* y,
+                                           int accumulate, double* tile_ss, thsp_stream_t stream);
 /* Same, with HOST x and y (pinned or pageable): H2D of x, kernel, D2H of y, then synchronises.
  * This is the call bench.py times for its end-to-end number. */
 THSP_API int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host,
@@ -213,6 +219,10 @@ THSP_API int thsp_dot_dev_f64(int64_t n, const double* x, const double* y, doubl
  * the binary tree over the index bits of the m partials (absent ones count as +0.0) into *out_dev.  The tree half also
  * combines the per-rank results of a partitioned vector (m = number of ranks). */
 THSP_API int thsp_tile_sumsq_f64(int64_t n, const double* y, double* tile_ss, thsp_stream_t stream);
+/* out[i] = x[i] * *scale_dev; *inv_dev = 1 / sqrt(*sumsq_dev) - the two halves of x = vec_axpby(1/sqrt(s), y, 0, y)
+ * with the scalar staying on the device (iterated loops that defer the normalisation into the next product) */
+THSP_API int thsp_scale_by_dev_f64(int64_t n, const double* x, const double* scale_dev, double* out, thsp_stream_t stream);
+THSP_API int thsp_inv_sqrt_dev_f64(const double* sumsq_dev, double* inv_dev, thsp_stream_t stream);
 THSP_API int thsp_tree_sum_f64(int64_t m, const double* vals, double* out_dev, thsp_stream_t stream);
 /* Order-independent 64-bit fingerprint of v[0..n) sitting at global index first_index of a longer vector: pieces add up
  * (mod 2^64) to the fingerprint of the whole.  bench.py compares row blocks on N GPUs with the one-GPU run. Synchronous. */
@@ -326,6 +336,15 @@ THSP_API int thsp_xchg_norm_scale_push_f64(int64_t n, const double* y, const dou
                                            void* const* peer_ctrl, void* work, double* x_local, int64_t offset, int ndest,
                                            double* const* dest_x, void* const* dest_ctrl, const int64_t* dest_lo,
                                            const int64_t* dest_hi, double* sumsq_out, thsp_stream_t stream);
+/* The step with the normalisation deferred into the next product (thsp_csr_plan_spmv_scaled_f64): y points at this rank's
+ * n rows (global rows offset .. offset+n), which ARE its slice of the next input vector.  Tree over tile_ss, partial
+ * published; the pieces [dest_lo[d], dest_hi[d]) of the raw y copied into dest_x[d] (the peers' replicas of the vector
+ * the NEXT product reads) and their flags raised; partials of all ranks combined: *sumsq_out = sum, *inv_out =
+ * 1/sqrt(sum) (device scalars).  The n-element vector is neither read nor written except for the pushed pieces. */
+THSP_API int thsp_xchg_norm_push_f64(int64_t n, const double* y, const double* tile_ss, uint64_t iter, int world, int rank,
+                                     void* const* peer_ctrl, void* work, int64_t offset, int ndest, double* const* dest_x,
+                                     void* const* dest_ctrl, const int64_t* dest_lo, const int64_t* dest_hi,
+                                     double* sumsq_out, double* inv_out, thsp_stream_t stream);
 /* stream-ordered wait until the ranks in src_mask have raised their halo flag for `iter` */
 THSP_API int thsp_xchg_wait(void* ctrl_local, uint64_t iter, unsigned src_mask, thsp_stream_t stream);
 /* *flag_host = 1 if a wait of this rank gave up (~15 s) instead of hanging the GPU */

@@ -40,14 +40,23 @@ class OracleOps:
     def csr_block(self, nrow, ncol, row_ptr, col_ind, values):
         return (nrow, ncol, row_ptr.numpy(), col_ind.numpy(), values.numpy()), int(col_ind.numel())
 
-    def spmv(self, payload, x, y, tile_ss=None):
+    def spmv(self, payload, x, y, tile_ss=None, xscale=None):
         nrow, ncol, rp, ci, va = payload
-        y.copy_(torch.from_numpy(self.O.csr_spmv(nrow, ncol, rp, ci, va, x.numpy(), np.zeros(nrow))))
+        xv = x.numpy()
+        if xscale is not None:   # csr_stream_kernel<kScale>: every gathered x_j times the scalar, one rounding
+            xv = xv * float(xscale[0])
+        y.copy_(torch.from_numpy(self.O.csr_spmv(nrow, ncol, rp, ci, va, xv, np.zeros(nrow))))
         if tile_ss is not None:   # the SpMV's epilogue: sum of squares per tile of 32 rows (csrc/tree_sum.cuh)
             tile_ss.copy_(torch.from_numpy(self.O.tile_sumsq(y.numpy())))
 
     def tree_sum(self, vals, out):
         out[0] = self.O.tree_sum(vals.numpy())
+
+    def inv_sqrt(self, ss, inv):
+        inv[0] = 1.0 / np.sqrt(float(ss[0]))
+
+    def scaled(self, x, scale):
+        return torch.from_numpy(x.numpy() * float(scale[0]))
 
     def hash(self, v, first):
         return self.O.hash_f64(v.numpy(), first)
@@ -84,6 +93,26 @@ class OracleOps:
 
     def wait_halo(self, it, src_mask):
         pass   # the emulated push below is synchronous
+
+    def xchg_dests2(self, dests, peer_ptr_sets):
+        self.dests = dests
+
+    def norm_push(self, y, tile_ss, it, xout, offset, ss, inv, which):
+        """thsp_xchg_norm_push_f64: the sum over all ranks and its 1/sqrt; the RAW pieces into the readers' copies"""
+        parts = [None] * self.xw
+        dist.all_gather_object(parts, self.O.tree_sum(tile_ss.numpy()))
+        tot = self.O.tree_sum(np.array(parts))
+        ss[0] = tot
+        inv[0] = 1.0 / np.sqrt(tot)
+        msgs = [(r, lo, hi, xout[lo:hi].clone()) for r, lo, hi in self.dests]
+        for m in msgs:
+            assert offset <= m[1] and m[2] <= offset + y.numel(), "a rank may only push pieces of its own slice"
+        allm = [None] * self.xw
+        dist.all_gather_object(allm, msgs)
+        for src, ms in enumerate(allm):
+            for r, lo, hi, data in ms:
+                if r == self.xr:
+                    xout[lo:hi] = data
 
     def norm_scale_push(self, y, tile_ss, it, x, offset, ss):
         parts = [None] * self.xw
@@ -129,7 +158,7 @@ def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
             A = power.PartitionedCSR.from_csr(n ** 3, torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va), rank, world, ops)
         else:
             A = power.PartitionedCSR.stencil27(n, rank, world, ops, max_block_rows=50)
-        it = power.PowerIteration(A, ops, exchange=mode, overlap=overlap, seed=5)
+        it = power.make_iteration(A, ops, exchange=mode, overlap=overlap, seed=5)
         for _ in range(steps):
             it.step()
         # after the last refresh every replica must hold the same, complete x (xchg: only the pieces it reads)
@@ -144,7 +173,9 @@ def _worker(rank, world, port, n, steps, mode, overlap, generic, out):
                                                           (2, 6, True, False, "xchg"), (3, 5, True, False, "xchg"),
                                                           (3, 6, False, True, "xchg"),
                                                           (2, 8, True, False, "xchg"), (4, 8, True, False, "allgather"),
-                                                          (2, 8, False, True, "allgather")])
+                                                          (2, 8, False, True, "allgather"),
+                                                          (2, 8, True, False, "xchgd"), (3, 5, True, False, "xchgd"),
+                                                          (2, 6, False, True, "xchgd"), (4, 8, True, False, "xchgd")])
 def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, overlap, generic, mode):
     steps = 4
     port = 29500 + (os.getpid() + world * 7 + n + len(mode)) % 400
@@ -172,7 +203,7 @@ def test_partitioned_power_iteration_matches_serial(oracle, tmp_path, world, n, 
                 assert hsum == oracle.hash_f64(y_one, 0)
         covered += res["count"]
         # rows are multiplied in the reference's order, so only the norm (a sum over ranks) differs in rounding
-        if mode == "xchg":   # a replica is refreshed only where this rank reads it: own slice + needed pieces
+        if mode in ("xchg", "xchgd"):   # a replica is refreshed only where this rank reads it: own slice + needed pieces
             xs = res["x"].numpy()
             for lo, hi in [(res["start"], res["start"] + res["count"])] + [(a, b) for _, a, b in res["needs"]]:
                 assert np.max(np.abs(xs[lo:hi] - x_ref[lo:hi])) <= 1e-13
