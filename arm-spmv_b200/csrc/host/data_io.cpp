@@ -78,9 +78,15 @@ void COOMatrixRead(const char* filename, COOMatrix& A)
     int rows = 0, cols = 0, nz = 0;
     if (mm_read_mtx_crd_size(fp, &rows, &cols, &nz) != 0) exit(1);
     printf("\tAllocating memory for matrix\n");
-    int* ri = alloc_matrix<int>(nz);
-    int* ci = alloc_matrix<int>(nz);
-    double* va = alloc_matrix<double>(nz);
+    int* ri = nullptr;
+    int* ci = nullptr;
+    double* va = nullptr;
+    {
+        Trace ta("  first CUDA call + allocation");
+        ri = alloc_matrix<int>(nz);
+        ci = alloc_matrix<int>(nz);
+        va = alloc_matrix<double>(nz);
+    }
     printf("\tReading matrix entries from file\n");
     bool on_gpu = false;
     const long pos = ftell(fp);
@@ -90,8 +96,14 @@ void COOMatrixRead(const char* filename, COOMatrix& A)
         if (end > pos) {
             const size_t len = (size_t)(end - pos);
             char* text = static_cast<char*>(malloc(len));
-            if (text && fread(text, 1, len, fp) == len) {
+            bool have = false;
+            {
+                Trace tf("  file into memory");
+                have = text && fread(text, 1, len, fp) == len;
+            }
+            if (have) {
                 int status = 1;
+                Trace tg("  entries parsed on the GPU");
                 if (thsp_mtx_parse_coo(text, len, nz, ri, ci, va, &status, nullptr) == 0 && status == 0) on_gpu = true;
                 printf(on_gpu ? "\tMatrix entries parsed on the GPU\n" : "\tMatrix entries need the scanf loop\n");
             }
