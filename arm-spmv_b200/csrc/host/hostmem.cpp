@@ -142,12 +142,24 @@ void sync() { ok(thsp_stream_sync(nullptr), "stream synchronise"); }
 
 void prefetch_traced(const void* p, size_t bytes)
 {
-    // Synchronise after each first-use prefetch: queuing several prefetches and a kernel behind
-    // them without waiting took 613 ms for 92 MB on the B200 box (driver 580), 2.8 ms with it.
+    // Managed pages the host has touched come back to the GPU here, once per array, in front of the first kernel that
+    // reads them.  cudaMemPrefetchAsync does that at ~35 GB/s - and on the B200 box (driver 580) one such call in every
+    // 3 to 15 takes 60-940 ms instead of 0.6 ms (profiles/r02_uvm_prefetch_probe.txt: any round, any array, with or
+    // without a warm-up; queuing several prefetches without waiting showed the same 613 ms in round 1).  In the reference's
+    // main.cpp that call sits INSIDE the timed COO loop (the host reads the COO arrays at :46-52 just before) and turned
+    // "### COO CPU GFLOPS" from 110 into 1 in half of the runs.  A kernel that simply READS the array lets the GPU's page
+    // faults pull the pages over: ~8 GB/s (2.7 ms for 21 MB), and the same in 8 of 8 runs.  THSP_PREFETCH=async brings
+    // cudaMemPrefetchAsync back.
+    static const bool async = getenv("THSP_PREFETCH") && !strcmp(getenv("THSP_PREFETCH"), "async");
     const double t0 = trace_on() ? now_ms() : 0.0;
-    ok(thsp_prefetch(p, bytes, 1, nullptr), "prefetch");
+    if (!async && bytes >= 16) {
+        uint64_t h = 0;
+        ok(thsp_hash_f64((int64_t)(bytes / 8), static_cast<const double*>(p), 0, &h, nullptr), "page touch");
+    } else {
+        ok(thsp_prefetch(p, bytes, 1, nullptr), "prefetch");
+    }
     ok(thsp_stream_sync(nullptr), "sync");
-    if (trace_on()) fprintf(stderr, "[thsp] prefetch %p %.1f MB: %.3f ms\n", p, bytes / 1e6, now_ms() - t0);
+    if (trace_on()) fprintf(stderr, "[thsp] %s %p %.1f MB: %.3f ms\n", async ? "prefetch" : "fault-in", p, bytes / 1e6, now_ms() - t0);
 }
 bool first_gpu_use(const void* p)
 {
