@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -124,15 +125,57 @@ struct GsEpilogue {
     V* x = nullptr;   // the same vector the kernel gathers from: rows of one colour never read each other's entries
 };
 
+// kFlow (thsp_csr_plan_spmv_host_f64, "flow" form): x is still arriving from the host - ONE copy, in flight - while the
+// kernel runs, and y is stored straight into the caller's page-locked vector.  Before the upload starts, the device
+// vector is filled with a NaN of a payload no computation produces; a value that still reads as that pattern has not
+// arrived.  A tile first waits (volatile loads, past L1) until the farthest column it gathers from is in, then gathers as
+// usual; every gathered value is compared with the pattern all the same - a copy does not promise to write in address
+// order - and the few that come back as the pattern are fetched again past L1 until they are in.  Waits give up after ~4 s
+// (an x that really contains the pattern: the host then runs the chunked form).
+struct FlowArgs {
+    const int* tile_need = nullptr;   // [tiles]: largest column the tile gathers from + 1
+    int* err = nullptr;               // pinned host word: a wait gave up
+    long long spin_limit = 8000000000LL;   // cycles a wait may take (THSP_FLOW_SPIN_CYCLES)
+};
+static constexpr unsigned long long kFlowPattern = 0x7FF85EEDC0DEF00DULL;   // a quiet NaN
+
+template <typename V>
+__device__ __forceinline__ bool flow_missing(V v)
+{
+    return false;
+}
+template <>
+__device__ __forceinline__ bool flow_missing<double>(double v)
+{
+    return (unsigned long long)__double_as_longlong(v) == kFlowPattern;
+}
+__device__ __forceinline__ double flow_reload(const double* p, const long long t0, int* err, const long long limit)
+{
+    // past L1 (the line may sit there in its not-yet-arrived state), until the copy has written it
+    for (unsigned polls = 1;; ++polls) {
+        double v;
+        asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+        if (!flow_missing(v)) return v;
+        // the flag lives in host memory: looked at once in 256 polls (somebody else gave up: no point in waiting on)
+        if (clock64() - t0 > limit || ((polls & 255u) == 0 && *reinterpret_cast<volatile int*>(err))) {
+            *reinterpret_cast<volatile int*>(err) = 1;
+            return v;   // the host sees the flag and discards the result
+        }
+        __nanosleep(200);
+    }
+}
+__device__ __forceinline__ float flow_reload(const float* p, const long long, int*, const long long) { return *p; }
+
 // kScale: every gathered x_j is multiplied by *xscale before it meets its matrix entry - y = A (s x) without a pass
 // that writes s x first.  The power iteration keeps its vector unnormalised and hands the SpMV 1/||y|| of the previous
 // step (power.py "deferred" modes): mul_rn(x_j, s) is the very product the normalising pass would have stored, so y has
 // the same bits, and one read and one write of the vector per iteration are gone.
-template <typename V, bool kGs, bool kScale>
+template <typename V, bool kGs, bool kScale, bool kFlow = false>
 __global__ void __launch_bounds__(768, 1)
     csr_stream_kernel(int nrow, int nnz, const int* __restrict__ row_ptr, const int* __restrict__ col,
                       const V* __restrict__ val, const V* __restrict__ x, V* __restrict__ y, int accumulate, int S, int CH,
-                      V* __restrict__ tile_ss, int* __restrict__ stale, GsEpilogue<V> gs, const V* __restrict__ xscale)
+                      V* __restrict__ tile_ss, int* __restrict__ stale, GsEpilogue<V> gs, const V* __restrict__ xscale,
+                      FlowArgs flow = FlowArgs())
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned full = 0xffffffffu;
@@ -256,8 +299,14 @@ __global__ void __launch_bounds__(768, 1)
                 gs_d = gs.diag[gs_i];
             }
         }
+        int flow_need = 0;
+        if (kFlow && c_chunk == 0) flow_need = __ldg(flow.tile_need + c_tile);   // in flight while the tile's entries arrive
         mbar_wait(bar + c_stage, c_parity);
         __syncwarp();
+        if (kFlow && c_chunk == 0 && flow_need > 0) {
+            if (lane == 0) (void)flow_reload(x + (flow_need - 1), clock64(), flow.err, flow.spin_limit);   // the farthest column is in
+            __syncwarp();
+        }
         {
             const int g0 = c_al + c_chunk * CH;
             const int g1 = min(g0 + CH, c_te);
@@ -273,6 +322,17 @@ __global__ void __launch_bounds__(768, 1)
                 for (int u = 0; u < U; ++u) cc[u] = (j + u < hi) ? sc[j + u] : 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) xx[u] = (j + u < hi) ? ld_gather(x + cc[u]) : V(0);
+                if (kFlow) {   // anything that has not arrived yet (rare: the tile has waited for its farthest column)
+                    bool missing = false;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) missing |= (j + u < hi) && flow_missing(xx[u]);
+                    if (missing) {
+                        const long long t0 = clock64();
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if ((j + u < hi) && flow_missing(xx[u])) xx[u] = flow_reload(x + cc[u], t0, flow.err, flow.spin_limit);
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) vv[u] = (j + u < hi) ? sv[j + u] : V(0);
 #pragma unroll
@@ -310,7 +370,7 @@ __global__ void __launch_bounds__(768, 1)
 template <typename V>
 static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const int* rp, const int* col, const V* val,
                       const V* x, V* y, int acc, cudaStream_t s, V* tile_ss = nullptr, int* stale = nullptr,
-                      GsEpilogue<V> gs = GsEpilogue<V>(), const V* xscale = nullptr)
+                      GsEpilogue<V> gs = GsEpilogue<V>(), const V* xscale = nullptr, const FlowArgs* flow = nullptr)
 {
     THSP_REQUIRE((((uintptr_t)val) & 15) == 0 && (((uintptr_t)col) & 15) == 0,
                  "csr stream kernel needs 16-byte aligned val/col_ind");
@@ -326,13 +386,15 @@ static int run_stream(const StreamCfg& cfg, int ctas, int nrow, int nnz, const i
         THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        THSP_CUDA(cudaFuncSetAttribute(csr_stream_kernel<V, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cur = 227 * 1024;
     }
     const int num_tiles = (nrow + 31) / 32;
     int grid = std::min(ctas, div_up(num_tiles, cfg.warps));
     if (grid < 1) grid = 1;
-    THSP_REQUIRE(!(gs.rows && xscale), "the Gauss-Seidel epilogue and a scaled x are not combined");
-    if (gs.rows) csr_stream_kernel<V, true, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr);
+    THSP_REQUIRE(!(gs.rows && xscale) && !(flow && (gs.rows || xscale)), "the Gauss-Seidel epilogue, a scaled x and the flow form are not combined");
+    if (flow) csr_stream_kernel<V, false, false, true><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr, *flow);
+    else if (gs.rows) csr_stream_kernel<V, true, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr);
     else if (xscale) csr_stream_kernel<V, false, true><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, xscale);
     else csr_stream_kernel<V, false, false><<<grid, cfg.warps * 32, smem, s>>>(nrow, nnz, rp, col, val, x, y, acc, cfg.stages, cfg.chunk, tile_ss, stale, gs, nullptr);
     THSP_LAUNCH_CHECK();
@@ -782,6 +844,56 @@ struct HostPipe {
     std::vector<cudaEvent_t> t_in, t_k0, t_k1, t_out;
 };
 
+// The "flow" form of the host-buffer call (stream kernel, y = A x, page-locked x and y): ONE upload of x, ONE persistent
+// launch that multiplies right behind the arriving x (csr_stream_kernel kFlow) and stores y straight into the caller's
+// page-locked vector - no pieces, no events between streams, nothing for y to queue behind.  The chunked form above keeps
+// y a whole chunk behind x on the link (with eleven chunks the call ends 0.4 ms after the last piece of x is in) and cannot
+// use smaller chunks: every separate copy costs ~12 us when both directions are busy (profiles/r01_e2e_chunks.txt; a
+// first flow form with 33 pieces + a 4-byte progress copy each measured 4.47 ms against 3.52 ms chunked).
+struct HostFlow {
+    int num_tiles = 0;
+    int x_lo = 0, x_hi = 0;      // rows of x the matrix reads: [smallest column, largest + 1)
+    int* tile_need = nullptr;    // device
+    int* range = nullptr;        // device scratch of the build
+    int* host_err = nullptr;     // pinned
+    cudaStream_t s_in = nullptr;
+    cudaEvent_t begin = nullptr, filled = nullptr, in_done = nullptr;
+};
+
+__global__ void __launch_bounds__(256) flow_fill_kernel(int64_t n, double* __restrict__ x)
+{
+    const double pat = __longlong_as_double((long long)kFlowPattern);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) x[i] = pat;
+}
+
+// need[tile] = largest column of the tile + 1; range[0] / range[1] = smallest column / largest column + 1 of the matrix
+__global__ void __launch_bounds__(256) tile_need_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col, int* __restrict__ need,
+                                                        int* __restrict__ range)
+{
+    const int tile = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    const int num_tiles = (nrow + 31) >> 5;
+    if (tile >= num_tiles) return;
+    const int e0 = rp[tile * 32], e1 = rp[min(tile * 32 + 32, nrow)];
+    int m = -1, lo = 0x7fffffff;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const int c = ld_stream(col + e);
+        m = max(m, c);
+        lo = min(lo, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if (lane == 0) {
+        need[tile] = m + 1;
+        if (m >= 0) {
+            atomicMin(range, lo);
+            atomicMax(range + 1, m + 1);
+        }
+    }
+}
+
 // Stale flags live in ONE pinned, device-mapped page per process: cudaHostAlloc costs 1-2 ms, which as a per-plan cost
 // landed inside main.cpp's 50-call timing loop (the first call creates the plan) and halved "### CSR CPU GFLOPS".
 static int* stale_slot_acquire()
@@ -821,6 +933,7 @@ void warm_stale_page() { stale_slot_acquire(); }   // thsp_prepare_conversions: 
 
 struct thsp_csr_plan {
     HostPipe* pipe = nullptr;
+    HostFlow* flow = nullptr;
     // Nothing here is derived from the contents of the arrays except nnz, the histogram and the kernel choice made from
     // it: the merge-path run table is recomputed by every call (one binary search per run, ~1 % of the kernel), and the
     // kernels that depend on nnz check it against row_ptr[nrow] and raise `stale` (pinned host memory the GPU can write).
@@ -987,9 +1100,24 @@ static void drop_host_pipe(thsp_csr_plan* plan)
     plan->pipe = nullptr;
 }
 
+static void drop_host_flow(thsp_csr_plan* plan)
+{
+    HostFlow* hf = plan->flow;
+    if (!hf) return;
+    if (hf->tile_need) cudaFree(hf->tile_need);
+    if (hf->range) cudaFree(hf->range);
+    if (hf->host_err) cudaFreeHost(hf->host_err);
+    for (cudaEvent_t e : {hf->begin, hf->filled, hf->in_done})
+        if (e) cudaEventDestroy(e);
+    if (hf->s_in) cudaStreamDestroy(hf->s_in);
+    delete hf;
+    plan->flow = nullptr;
+}
+
 int thsp_csr_plan_destroy(thsp_csr_plan* plan)
 {
     if (plan) drop_host_pipe(plan);
+    if (plan) drop_host_flow(plan);
     delete plan;
     return 0;
 }
@@ -1243,6 +1371,61 @@ static int host_pipe_enqueue(thsp_csr_plan* plan, const double* x_host, double* 
     return 0;
 }
 
+static int build_host_flow(thsp_csr_plan* p, cudaStream_t s)
+{
+    HostFlow* hf = new HostFlow();
+    p->flow = hf;
+    hf->num_tiles = (p->nrow + 31) / 32;
+    THSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&hf->tile_need), sizeof(int) * (size_t)hf->num_tiles));
+    THSP_CUDA(cudaMalloc(reinterpret_cast<void**>(&hf->range), sizeof(int) * 2));
+    THSP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hf->host_err), sizeof(int) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    hf->host_err[0] = 0;
+    // which rows of x the matrix reads at all (a row block of a partitioned matrix reads a window), and per tile how far
+    int range[2] = {0x7fffffff, 0};
+    THSP_CUDA(cudaMemcpyAsync(hf->range, range, sizeof(range), cudaMemcpyHostToDevice, s));
+    tile_need_kernel<<<div_up((int64_t)hf->num_tiles * 32, 256), 256, 0, s>>>(p->nrow, p->row_ptr, p->col_ind, hf->tile_need, hf->range);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaMemcpyAsync(range, hf->range, sizeof(range), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    hf->x_hi = std::min(range[1], p->ncol);
+    hf->x_lo = std::min(range[0], hf->x_hi);
+    THSP_CUDA(cudaStreamCreateWithFlags(&hf->s_in, cudaStreamNonBlocking));
+    THSP_CUDA(cudaEventCreateWithFlags(&hf->begin, cudaEventDisableTiming));
+    THSP_CUDA(cudaEventCreateWithFlags(&hf->filled, cudaEventDisableTiming));
+    THSP_CUDA(cudaEventCreateWithFlags(&hf->in_done, cudaEventDisableTiming));
+    return 0;
+}
+
+// One call in the flow form; returns 0 when y is in host memory, 3 when a wait gave up (the caller runs the chunked form).
+static int host_flow_run(thsp_csr_plan* plan, const double* x_host, double* y_host_dev, double* x_dev, cudaStream_t s)
+{
+    HostFlow* hf = plan->flow;
+    hf->host_err[0] = 0;
+    const int64_t n = (int64_t)hf->x_hi - hf->x_lo;
+    THSP_CUDA(cudaEventRecord(hf->begin, s));   // earlier work on the scratch vector
+    THSP_CUDA(cudaStreamWaitEvent(hf->s_in, hf->begin, 0));
+    if (n > 0) {
+        flow_fill_kernel<<<std::min(div_up(n, 256 * 8), sm_count() * 8), 256, 0, hf->s_in>>>(n, x_dev + hf->x_lo);
+        THSP_LAUNCH_CHECK();
+    }
+    THSP_CUDA(cudaEventRecord(hf->filled, hf->s_in));
+    if (n > 0)   // the one upload, right behind the fill on the same stream
+        THSP_CUDA(cudaMemcpyAsync(x_dev + hf->x_lo, x_host + hf->x_lo, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, hf->s_in));
+    THSP_CUDA(cudaEventRecord(hf->in_done, hf->s_in));
+    THSP_CUDA(cudaStreamWaitEvent(s, hf->filled, 0));   // the kernel must not see what an earlier call left in x_dev
+    FlowArgs fa;
+    fa.tile_need = hf->tile_need;
+    fa.err = hf->host_err;
+    if (const char* e = getenv("THSP_FLOW_SPIN_CYCLES")) fa.spin_limit = std::max(1000000LL, atoll(e));
+    if (run_stream<double>(plan->stream_cfg, plan->ctas, plan->nrow, plan->nnz, plan->row_ptr, plan->col_ind,
+                           static_cast<const double*>(plan->val), x_dev, y_host_dev, 0, s, nullptr, plan->stale, GsEpilogue<double>(), nullptr, &fa))
+        return 1;
+    THSP_CUDA(cudaStreamWaitEvent(s, hf->in_done, 0));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    if (*static_cast<volatile int*>(hf->host_err)) return 3;
+    return 0;
+}
+
 static bool is_pinned_host(const void* p)
 {
     cudaPointerAttributes a;
@@ -1260,6 +1443,18 @@ int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* cplan, const double* x_host
     thsp_csr_plan* plan = const_cast<thsp_csr_plan*>(cplan);
     cudaStream_t s = as_stream(stream);
     if (plan->nrow <= 0) return 0;
+    static const int env_flow = getenv("THSP_HOST_FLOW") ? atoi(getenv("THSP_HOST_FLOW")) : 1;
+    if (env_flow && !accumulate && plan->kernel == THSP_CSR_STREAM && plan->nrow >= (1 << 21) && is_pinned_host(x_host)) {
+        void* y_map = nullptr;   // the kernel stores y through the device's view of the caller's page-locked vector
+        if (is_pinned_host(y_host) && cudaHostGetDevicePointer(&y_map, y_host, 0) == cudaSuccess && y_map) {
+            if (!plan->flow && build_host_flow(plan, s)) return 1;
+            const int rc = host_flow_run(plan, x_host, static_cast<double*>(y_map), x_dev, s);
+            if (rc != 3) return rc;
+            // a wait gave up: x holds the very NaN the flow form marks missing values with (or the upload failed) - chunked form
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (plan->pipe) {
         const HostPipe* b = plan->pipe;
         if (b->built_kernel != plan->kernel || b->built_lanes != plan->lanes || b->built_ctas != plan->ctas ||

@@ -141,7 +141,12 @@ THSP_API int thsp_csr_plan_spmv_sumsq_f64(const thsp_csr_plan* plan, const doubl
 THSP_API int thsp_csr_plan_spmv_scaled_f64(const thsp_csr_plan* plan, const double* x, const double* xscale, double* y,
                                            int accumulate, double* tile_ss, thsp_stream_t stream);
 /* Same, with HOST x and y (pinned or pageable): H2D of x, kernel, D2H of y, then synchronises.
- * This is the call bench.py times for its end-to-end number. */
+ * This is the call bench.py times for its end-to-end number.  Two forms: row chunks pipelined over three streams (any
+ * kernel, pageable buffers, y += A x), and - stream kernel, y = A x, page-locked x and y, >= 2 M rows - the "flow" form:
+ * one upload of x, one persistent launch that multiplies right behind the arriving x and stores y straight into y_host
+ * (x_dev_scratch is pre-filled with a NaN pattern that marks values not yet arrived; an x that contains that very
+ * pattern, 0x7FF85EEDC0DEF00D, makes the form give up after ~4 s and the chunked form run instead).  THSP_HOST_FLOW=0
+ * selects the chunked form always.  y_dev_scratch is not touched by the flow form. */
 THSP_API int thsp_csr_plan_spmv_host_f64(const thsp_csr_plan* plan, const double* x_host, double* y_host,
                                          double* x_dev_scratch, double* y_dev_scratch, int accumulate,
                                          thsp_stream_t stream);

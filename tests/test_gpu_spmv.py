@@ -338,3 +338,43 @@ def test_ell_fp32(thsp, cuda, oracle, nrow_pad):
     ref64 = oracle.ell_spmv(nrow, ncol, k, eco, v32.astype(np.float64), x.astype(np.float64), y0.astype(np.float64))
     scale = row_scale_coo(nrow, ri, ci, va.astype(np.float32).astype(np.float64), x.astype(np.float64))
     assert max_row_error(host(y).astype(np.float64), ref64, scale, y0.astype(np.float64)) <= TOL32
+
+
+def test_csr_host_buffer_flow_form(thsp, cuda, oracle, monkeypatch):
+    """thsp_csr_plan_spmv_host_f64, flow form (stream kernel, y = A x, page-locked x and y, >= 2 M rows): one upload of x,
+    one launch that multiplies behind the arriving x and stores y into the caller's vector.  Same bits as the device path
+    and the oracle, call after call with changing x; an x that contains the NaN pattern the form marks missing values
+    with makes it give up (here after 5 ms instead of 4 s) and the chunked form answers - same bits again."""
+    import ctypes
+    from arm_spmv_b200 import host as H
+    n = 128
+    nrow = n ** 3
+    A = H.stencil27_csr(n)
+    assert A.plan_kernel()[0] == "stream"
+    rp, ci, va = oracle.gen_stencil27_csr(n)
+    lib = thsp.load()
+    xd = torch.full((nrow,), float("nan"), dtype=torch.float64, device="cuda")
+    yd = torch.full((nrow,), float("nan"), dtype=torch.float64, device="cuda")
+    xh = torch.empty(nrow, dtype=torch.float64).pin_memory()
+    yh = torch.empty(nrow, dtype=torch.float64).pin_memory()
+    for it in range(4):
+        x = oracle.gen_vector(nrow, 50 + it) - 0.25 * it
+        xh.copy_(torch.from_numpy(x))
+        yh.fill_(float("nan"))
+        l0 = thsp.lib.launch_count()
+        thsp.lib.check(lib.thsp_csr_plan_spmv_host_f64(A.plan(), ctypes.c_void_p(xh.data_ptr()), ctypes.c_void_p(yh.data_ptr()),
+                                                       thsp.lib.ptr(xd), thsp.lib.ptr(yd), 0, thsp.lib.current_stream()))
+        assert thsp.lib.launch_count() - l0 == (3 if it == 0 else 2), "the flow form is one fill and one SpMV launch (+ the first call's look at the columns)"
+        assert_bits(yh.numpy(), oracle.csr_spmv(nrow, nrow, rp, ci, va, x, np.zeros(nrow)), f"flow form, call {it}")
+    # x holds the pattern itself: the flow form cannot tell it from "not arrived", gives up, the chunked form runs
+    monkeypatch.setenv("THSP_FLOW_SPIN_CYCLES", "10000000")
+    x = oracle.gen_vector(nrow, 77)
+    x[nrow // 3] = np.frombuffer(np.uint64(0x7FF85EEDC0DEF00D).tobytes(), dtype=np.float64)[0]
+    xh.copy_(torch.from_numpy(x))
+    yh.fill_(0.0)
+    thsp.lib.check(lib.thsp_csr_plan_spmv_host_f64(A.plan(), ctypes.c_void_p(xh.data_ptr()), ctypes.c_void_p(yh.data_ptr()),
+                                                   thsp.lib.ptr(xd), thsp.lib.ptr(yd), 0, thsp.lib.current_stream()))
+    Y = H.Vector(np.zeros(nrow)); H.CSRMatrixMatVector(A, H.Vector(x), Y, False)
+    got, want = yh.numpy(), host(Y.values)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).sum() == 27
+    assert_bits(got[~np.isnan(got)], want[~np.isnan(want)], "chunked form after the flow form gave up")
