@@ -68,8 +68,17 @@ void* scratch(size_t bytes, int slot)
     ++s.uses;
     if (s.cap < bytes) {
         if (s.p) {
-            cudaDeviceSynchronize();
+            // growing frees the old buffer, which earlier launches may still use: wait for them.  Not possible while this
+            // thread captures a stream (the wait is refused and a pointer baked into a graph would dangle): fail loudly.
+            const cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("scratch slot %d cannot grow from %zu to %zu bytes here: %s (stream capture active?)", slot, s.cap, bytes,
+                          cudaGetErrorString(e));
+                return nullptr;
+            }
             cudaFree(s.p);
+            s.p = nullptr;
         }
         size_t cap = bytes < 4096 ? 4096 : bytes;
         if (cudaMalloc(&s.p, cap) != cudaSuccess) {

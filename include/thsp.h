@@ -70,6 +70,10 @@ THSP_API int thsp_stream_sync(thsp_stream_t stream);
 THSP_API int thsp_device_sync(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 THSP_API uint64_t thsp_launch_count(void);
+/* Scratch (partials of reductions, merge-path carries, the products of the two-phase COO path, the buffers of the
+ * conversions) is kept per DEVICE, not per stream: calls that need it must not run at the same time on different streams
+ * or host threads of one device - like the reference, whose conversions and products are not re-entrant either
+ * (SURVEY.md 8b).  A buffer that has to grow waits for the device first and refuses to grow inside a stream capture. */
 /* Frees the library's scratch buffers on the current device (they grow to the largest call seen:
  * sort buffers of a conversion, staged text of the reader).  The next call re-allocates. */
 THSP_API int thsp_scratch_release(void);
