@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kDiaRows) dia_kernel(int row_begin, int nrows,
 // A warp keeps two stages: the next tile is in flight while the current one is consumed.
 static constexpr int kDiaMaxOff = 64;   // offsets cached in shared memory; wider matrices use dia_kernel
 
-__global__ void __launch_bounds__(768, 1)
+__global__ void __launch_bounds__(1024, 1)
     dia_stream_kernel(int row_begin, int nrows, int nrow_total, int ndiags, const int* __restrict__ off,
                       const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, int stage_elems,
                       int S)
@@ -693,7 +693,10 @@ int thsp_dia_spmv_rows_f64(int row_begin, int row_count, int nrow, int ndiags, c
         static const int env_stages = getenv("THSP_DIA_STAGES") ? atoi(getenv("THSP_DIA_STAGES")) : 0;
         const int S = env_stages == 1 || env_stages == 2 ? env_stages : 1;   // like CSR: warps in flight beat ring depth
         const size_t per_warp = (size_t)S * stage_elems * sizeof(double) + 2 * sizeof(uint64_t);
-        int warps = (int)std::min<size_t>(24, (216 * 1024) / per_warp);
+        // as many warps as the stages leave room for (up to 32): the tile's chain - bulk copy, 27 gathers, in-order adds - is
+        // bound by latency, and on the 256^3 stencil 16 / 20 / 24 / 28 / 31 warps take 0.772 / 0.711 / 0.688 / 0.646 / 0.613 ms
+        static const int env_warps = getenv("THSP_DIA_WARPS") ? atoi(getenv("THSP_DIA_WARPS")) : 0;
+        int warps = (int)std::min<size_t>(env_warps > 0 ? std::min(env_warps, 32) : 32, (216 * 1024) / per_warp);
         if (warps >= 4) {
             const size_t smem = per_warp * warps;
             static bool configured[16] = {};
