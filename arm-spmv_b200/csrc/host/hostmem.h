@@ -33,7 +33,8 @@ inline T* alloc(size_t n)
 
 // Matrix arrays.  (Tried: cudaMemAdviseSetReadMostly, so that the host loop of main.cpp:46-52 would leave the copy in HBM
 // valid.  Measured on B200 / driver 580: kernels WRITING such arrays - every conversion, the GPU parser - crawl, COO->CSC of
-// 5.2 M entries 4.8 -> 883 ms, the whole driver run 2.3 -> 4.6 s.  Plain managed memory it is.)
+// 5.2 M entries 4.8 -> 883 ms, the whole driver run 2.3 -> 4.6 s.  Plain managed memory it is - except for the COO arrays of
+// COOMatrixRead, which are marked AFTER the parser has written them: data_io.cpp.)
 template <class T>
 inline T* alloc_matrix(size_t n)
 {

@@ -217,6 +217,13 @@ int thsp_prefetch(const void* p, size_t bytes, int to_device, thsp_stream_t s)
     THSP_CUDA(cudaMemPrefetchAsync(p, bytes, to_device ? dev : cudaCpuDeviceId, as_stream(s)));
     return 0;
 }
+int thsp_advise_read_mostly(const void* managed_ptr, size_t bytes, int on)
+{
+    int dev = 0;
+    THSP_CUDA(cudaGetDevice(&dev));
+    if (bytes) THSP_CUDA(cudaMemAdvise(managed_ptr, bytes, on ? cudaMemAdviseSetReadMostly : cudaMemAdviseUnsetReadMostly, dev));
+    return 0;
+}
 int thsp_stream_sync(thsp_stream_t s)
 {
     THSP_CUDA(cudaStreamSynchronize(as_stream(s)));

@@ -66,6 +66,10 @@ THSP_API int thsp_memcpy_d2h(void* dst_host, const void* src, size_t bytes, thsp
 THSP_API int thsp_memcpy_d2d(void* dst, const void* src, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_memset(void* dst, int byte, size_t bytes, thsp_stream_t stream);
 THSP_API int thsp_prefetch(const void* managed_ptr, size_t bytes, int to_device, thsp_stream_t stream);
+/* cudaMemAdviseSetReadMostly (on = 1) / Unset (on = 0) on a managed range that is COMPLETE: host reads then leave the copy
+ * in HBM valid (the reference's main.cpp:46-52 reads the COO arrays on the host between the reader and the first product).
+ * Not for arrays a kernel still has to write: writes to read-mostly pages are extremely slow. */
+THSP_API int thsp_advise_read_mostly(const void* managed_ptr, size_t bytes, int on);
 THSP_API int thsp_stream_sync(thsp_stream_t stream);
 THSP_API int thsp_device_sync(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
