@@ -272,11 +272,22 @@ __global__ void __launch_bounds__(256) tile_dot_kernel(int64_t n, const double* 
     const int lane = threadIdx.x & 31;
     const int64_t ntiles = (n + 31) >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, GW = ((int64_t)gridDim.x * 256) >> 5;
-    for (int64_t t = gw; t < ntiles; t += GW) {
-        const int64_t i = t * 32 + lane;
-        const double p = i < n ? mul_rn(ld_stream(a + i), ld_stream(b + i)) : 0.0;
-        const double q = warp_butterfly_sum(p);
-        if (lane == 0) tile[t] = q;
+    // four tiles per trip: eight loads in flight per lane (one tile per trip left the kernel waiting on latency: 3.6 TB/s)
+    constexpr int U = 4;
+    for (int64_t t0 = gw; t0 < ntiles; t0 += U * GW) {
+        double va[U], vb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = (t0 + u * GW) * 32 + lane;
+            const bool in = t0 + u * GW < ntiles && i < n;
+            va[u] = in ? ld_stream(a + i) : 0.0;
+            vb[u] = in ? ld_stream(b + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double q = warp_butterfly_sum(mul_rn(va[u], vb[u]));
+            if (lane == 0 && t0 + u * GW < ntiles) tile[t0 + u * GW] = q;
+        }
     }
 }
 // s[2] = s[0] / s[1]; s[3] = -s[2]         (alpha = rz / pAp)
@@ -294,30 +305,56 @@ __global__ void cg_beta_kernel(double* s)
 }
 // Vector::AddScaled (src/vector.cpp:98-128) with the scalar on the device: v += a x in the general form (a = +-1 give
 // the same bits as the reference's special branches, a = 0 leaves v alone as there)
+// Four consecutive elements per thread, 16-byte accesses when both arrays allow it (vec_ops.cu map_kernel: one element per
+// access reaches 4-5 TB/s on these two-stream and in-place shapes, 16-byte accesses 6.5-6.9 TB/s).
+template <class G>
+__device__ __forceinline__ void map2_inplace(int64_t n, const double* __restrict__ x, double* __restrict__ v, G g)
+{
+    const bool vec = ((((uintptr_t)x) | ((uintptr_t)v)) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < n; base += stride) {
+        if (vec && base + 4 <= n) {
+            const double2 x0 = *reinterpret_cast<const double2*>(x + base), x1 = *reinterpret_cast<const double2*>(x + base + 2);
+            const double2 v0 = *reinterpret_cast<const double2*>(v + base), v1 = *reinterpret_cast<const double2*>(v + base + 2);
+            *reinterpret_cast<double2*>(v + base) = make_double2(g(v0.x, x0.x), g(v0.y, x0.y));
+            *reinterpret_cast<double2*>(v + base + 2) = make_double2(g(v1.x, x1.x), g(v1.y, x1.y));
+        } else {
+            for (int k = 0; k < 4 && base + k < n; ++k) v[base + k] = g(v[base + k], x[base + k]);
+        }
+    }
+}
 __global__ void __launch_bounds__(256) add_scaled_dev_kernel(int64_t n, const double* __restrict__ a_dev, const double* __restrict__ x,
                                                              double* __restrict__ v)
 {
     const double a = *a_dev;
     if (a == 0.0) return;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) v[i] = add_rn(v[i], mul_rn(a, x[i]));
+    map2_inplace(n, x, v, [a](double vi, double xi) { return add_rn(vi, mul_rn(a, xi)); });
 }
 // vec_axpby(1, z, beta, p, p): the alpha == 1 branch (src/vec_vec.cpp:54-61): w = beta y + x
 __global__ void __launch_bounds__(256) xpby_dev_kernel(int64_t n, const double* __restrict__ z, const double* __restrict__ beta_dev,
                                                        double* __restrict__ p)
 {
     const double b = *beta_dev;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) p[i] = add_rn(mul_rn(b, p[i]), z[i]);
+    map2_inplace(n, z, p, [b](double pi, double zi) { return add_rn(mul_rn(b, pi), zi); });
 }
 __global__ void __launch_bounds__(256) jacobi_apply_kernel(int64_t n, const double* __restrict__ d, const double* __restrict__ r,
                                                            double* __restrict__ z)
 {
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) z[i] = __ddiv_rn(r[i], d[i]);
+    const bool vec = ((((uintptr_t)d) | ((uintptr_t)r) | ((uintptr_t)z)) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; base < n; base += stride) {
+        if (vec && base + 4 <= n) {
+            const double2 r0 = *reinterpret_cast<const double2*>(r + base), r1 = *reinterpret_cast<const double2*>(r + base + 2);
+            const double2 d0 = *reinterpret_cast<const double2*>(d + base), d1 = *reinterpret_cast<const double2*>(d + base + 2);
+            *reinterpret_cast<double2*>(z + base) = make_double2(__ddiv_rn(r0.x, d0.x), __ddiv_rn(r0.y, d0.y));
+            *reinterpret_cast<double2*>(z + base + 2) = make_double2(__ddiv_rn(r1.x, d1.x), __ddiv_rn(r1.y, d1.y));
+        } else {
+            for (int k = 0; k < 4 && base + k < n; ++k) z[base + k] = __ddiv_rn(r[base + k], d[base + k]);
+        }
+    }
 }
 
-static inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>((int64_t)sm_count() * 8, std::max<int64_t>(1, (n + 1023) / 1024)); }
+static inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>((int64_t)sm_count() * 2048, std::max<int64_t>(1, (n + 1023) / 1024)); }
 
 }  // namespace thsp
 

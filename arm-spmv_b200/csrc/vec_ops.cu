@@ -4,8 +4,7 @@
 // AddScaled,Add2Scaled}, checkVector (src/vector.cpp:59-171).
 // Elementwise kernels use unfused mul/add (common.cuh) and the reference's branch structure,
 // so their outputs are bit-identical to the reference.  All are pure streaming kernels
-// (HBM-bound): 256-thread CTAs, 4 independent elements in flight per thread, grid sized to a
-// multiple of the SM count.
+// (HBM-bound): 256-thread CTAs, four consecutive elements per thread moved with 16-byte accesses (map_kernel).
 #include <algorithm>
 
 #include "common.cuh"
@@ -41,6 +40,74 @@ static int launch_ew(int64_t n, cudaStream_t s, F f)
 {
     if (n <= 0) return 0;
     ew_kernel<<<ew_grid(n), kEwThreads, 0, s>>>(n, f);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- elementwise maps out[i] = g(a[i], b[i], c[i]) with 128-bit accesses -------------------------------------------------
+// A thread owns FOUR consecutive elements and moves them as one 32-byte access per array (two 16-byte ones when the arrays
+// are only 16-byte aligned); a CTA owns 1024 consecutive elements.  The first form of these kernels (ew_kernel
+// above: one element per access, four accesses 2.4 MB apart per thread) reached the HBM roofline only with two input
+// streams - 6.6 TB/s for w = a x + b y, but 4.0 TB/s for w = a x and 4.9 TB/s for the in-place v += a x on 134 M
+// doubles (scripts/vec_bench.py, profiles/r02_vec_ops.txt); with 16-byte accesses all of them run at 6.5-6.9 TB/s.
+// out may alias an input (in-place updates): a thread reads its four elements before it writes them.
+static constexpr int kMapThreads = 256;
+static constexpr int kMapPer = 4;
+
+// four consecutive doubles as ONE 32-byte access (sm_100: LDG.E.256 / STG.E.256 - a whole sector per thread, so no store ever
+// covers half a sector), as two 16-byte accesses, or one by one
+__device__ __forceinline__ void load4(const double* p, int vec, double (&v)[4])
+{
+    if (vec == 2) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+__device__ __forceinline__ void store4(double* p, int vec, const double (&v)[4])
+{
+    if (vec == 2) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    } else {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    }
+}
+
+template <int NIN, class G>
+__global__ void __launch_bounds__(kMapThreads) map_kernel(int64_t n, double* out, const double* a, const double* b, const double* c, G g,
+                                                          int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * kMapThreads * kMapPer;
+    for (int64_t base = ((int64_t)blockIdx.x * kMapThreads + threadIdx.x) * kMapPer; base < n; base += stride) {
+        double va[kMapPer] = {0, 0, 0, 0}, vb[kMapPer] = {0, 0, 0, 0}, vc[kMapPer] = {0, 0, 0, 0}, r[kMapPer];
+        if (vec && base + kMapPer <= n) {
+            if (NIN >= 1) load4(a + base, vec, va);
+            if (NIN >= 2) load4(b + base, vec, vb);
+            if (NIN >= 3) load4(c + base, vec, vc);
+#pragma unroll
+            for (int k = 0; k < kMapPer; ++k) r[k] = g(va[k], vb[k], vc[k]);
+            store4(out + base, vec, r);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kMapPer; ++k)
+                if (base + k < n) {
+                    const double xa = NIN >= 1 ? a[base + k] : 0.0, xb = NIN >= 2 ? b[base + k] : 0.0, xc = NIN >= 3 ? c[base + k] : 0.0;
+                    out[base + k] = g(xa, xb, xc);
+                }
+        }
+    }
+}
+
+template <int NIN, class G>
+static int launch_map(int64_t n, cudaStream_t s, double* out, const double* a, const double* b, const double* c, G g)
+{
+    if (n <= 0) return 0;
+    const uintptr_t bits = (uintptr_t)out | (NIN >= 1 ? (uintptr_t)a : 0) | (NIN >= 2 ? (uintptr_t)b : 0) | (NIN >= 3 ? (uintptr_t)c : 0);
+    const int64_t ctas = (n + (int64_t)kMapThreads * kMapPer - 1) / ((int64_t)kMapThreads * kMapPer);
+    const int grid = (int)std::min<int64_t>(ctas, (int64_t)sm_count() * 2048);   // one pass for anything below 300 M elements
+    map_kernel<NIN, G><<<grid, kMapThreads, 0, s>>>(n, out, a, b, c, g, (bits & 31) == 0 ? 2 : ((bits & 15) == 0 ? 1 : 0));
     THSP_LAUNCH_CHECK();
     return 0;
 }
@@ -146,11 +213,19 @@ __global__ void __launch_bounds__(256) tile_sumsq_kernel(int64_t n, const double
     const int lane = threadIdx.x & 31;
     const int64_t ntiles = (n + 31) >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, GW = ((int64_t)gridDim.x * 256) >> 5;
-    for (int64_t t = gw; t < ntiles; t += GW) {
-        const int64_t i = t * 32 + lane;
-        const double v = i < n ? ld_stream(y + i) : 0.0;
-        const double q = warp_butterfly_sum(mul_rn(v, v));
-        if (lane == 0) tile_ss[t] = q;
+    constexpr int U = 4;   // four tiles per trip: four loads in flight per lane
+    for (int64_t t0 = gw; t0 < ntiles; t0 += U * GW) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = (t0 + u * GW) * 32 + lane;
+            v[u] = (t0 + u * GW < ntiles && i < n) ? ld_stream(y + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double q = warp_butterfly_sum(mul_rn(v[u], v[u]));
+            if (lane == 0 && t0 + u * GW < ntiles) tile_ss[t0 + u * GW] = q;
+        }
     }
 }
 __global__ void __launch_bounds__(kTreeThreads) tree_blocks_kernel(int64_t m, const double* __restrict__ vals, double* __restrict__ out)
@@ -196,7 +271,8 @@ int thsp_csr_diagonal_f64(int nrow, const int* row_ptr, const int* col_ind, cons
 int thsp_jacobi_update_f64(int64_t n, double omega, const double* diag, const double* r, double* x, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { x[i] = add_rn(x[i], mul_rn(omega, __ddiv_rn(r[i], diag[i]))); });
+    return launch_map<3>(n, as_stream(stream), x, x, r, diag,
+                         [=] __device__(double xi, double ri, double di) { return add_rn(xi, mul_rn(omega, __ddiv_rn(ri, di))); });
 }
 
 int thsp_dot_dev_f64(int64_t n, const double* x, const double* y, double* result_dev, thsp_stream_t stream)
@@ -263,7 +339,7 @@ int thsp_tree_sum_f64(int64_t m, const double* vals, double* out_dev, thsp_strea
 int thsp_scale_by_dev_f64(int64_t n, const double* x, const double* scale_dev, double* out, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { out[i] = mul_rn(x[i], __ldg(scale_dev)); });
+    return launch_map<1>(n, as_stream(stream), out, x, nullptr, nullptr, [=] __device__(double xi, double, double) { return mul_rn(xi, __ldg(scale_dev)); });
 }
 // *inv = 1 / sqrt(*sumsq): the factor of vec_axpby(1/sqrt(s), y, 0, y), left on the device for the next product
 int thsp_inv_sqrt_dev_f64(const double* sumsq_dev, double* inv_dev, thsp_stream_t stream)
@@ -276,34 +352,34 @@ int thsp_axpby_f64(int64_t n, double alpha, const double* x, double beta, const 
     if (ensure_device()) return 1;
     cudaStream_t s = as_stream(stream);
     // Branch order and per-branch expression follow src/vec_vec.cpp:38-93.
-    if (alpha == 0) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = mul_rn(beta, y[i]); });
-    if (beta == 0) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = mul_rn(alpha, x[i]); });
-    if (alpha == 1) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = add_rn(mul_rn(beta, y[i]), x[i]); });
-    if (alpha == -1) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = add_rn(mul_rn(beta, y[i]), -x[i]); });
-    if (beta == 1) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = add_rn(mul_rn(alpha, x[i]), y[i]); });
-    if (beta == -1) return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = add_rn(mul_rn(alpha, x[i]), -y[i]); });
-    return launch_ew(n, s, [=] __device__(int64_t i) { w[i] = add_rn(mul_rn(alpha, x[i]), mul_rn(beta, y[i])); });
+    if (alpha == 0) return launch_map<1>(n, s, w, y, nullptr, nullptr, [=] __device__(double yi, double, double) { return mul_rn(beta, yi); });
+    if (beta == 0) return launch_map<1>(n, s, w, x, nullptr, nullptr, [=] __device__(double xi, double, double) { return mul_rn(alpha, xi); });
+    if (alpha == 1) return launch_map<2>(n, s, w, x, y, nullptr, [=] __device__(double xi, double yi, double) { return add_rn(mul_rn(beta, yi), xi); });
+    if (alpha == -1) return launch_map<2>(n, s, w, x, y, nullptr, [=] __device__(double xi, double yi, double) { return add_rn(mul_rn(beta, yi), -xi); });
+    if (beta == 1) return launch_map<2>(n, s, w, x, y, nullptr, [=] __device__(double xi, double yi, double) { return add_rn(mul_rn(alpha, xi), yi); });
+    if (beta == -1) return launch_map<2>(n, s, w, x, y, nullptr, [=] __device__(double xi, double yi, double) { return add_rn(mul_rn(alpha, xi), -yi); });
+    return launch_map<2>(n, s, w, x, y, nullptr, [=] __device__(double xi, double yi, double) { return add_rn(mul_rn(alpha, xi), mul_rn(beta, yi)); });
 }
 
 int thsp_fill_f64(int64_t n, double a, double* v, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { v[i] = a; });
+    return launch_map<0>(n, as_stream(stream), v, nullptr, nullptr, nullptr, [=] __device__(double, double, double) { return a; });
 }
 int thsp_scale_f64(int64_t n, double a, double* v, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { v[i] = mul_rn(v[i], a); });
+    return launch_map<1>(n, as_stream(stream), v, v, nullptr, nullptr, [=] __device__(double vi, double, double) { return mul_rn(vi, a); });
 }
 int thsp_shift_f64(int64_t n, double a, double* v, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { v[i] = add_rn(v[i], a); });
+    return launch_map<1>(n, as_stream(stream), v, v, nullptr, nullptr, [=] __device__(double vi, double, double) { return add_rn(vi, a); });
 }
 int thsp_copy_f64(int64_t n, const double* x, double* v, thsp_stream_t stream)
 {
     if (ensure_device()) return 1;
-    return launch_ew(n, as_stream(stream), [=] __device__(int64_t i) { v[i] = x[i]; });
+    return launch_map<1>(n, as_stream(stream), v, x, nullptr, nullptr, [=] __device__(double xi, double, double) { return xi; });
 }
 int thsp_add_scaled_f64(int64_t n, double a, const double* x, double* v, thsp_stream_t stream)
 {
@@ -311,9 +387,9 @@ int thsp_add_scaled_f64(int64_t n, double a, const double* x, double* v, thsp_st
     cudaStream_t s = as_stream(stream);
     // src/vector.cpp:98-128
     if (a == 0) return 0;
-    if (a == 1) return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], x[i]); });
-    if (a == -1) return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], -x[i]); });
-    return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], mul_rn(a, x[i])); });
+    if (a == 1) return launch_map<2>(n, s, v, v, x, nullptr, [=] __device__(double vi, double xi, double) { return add_rn(vi, xi); });
+    if (a == -1) return launch_map<2>(n, s, v, v, x, nullptr, [=] __device__(double vi, double xi, double) { return add_rn(vi, -xi); });
+    return launch_map<2>(n, s, v, v, x, nullptr, [=] __device__(double vi, double xi, double) { return add_rn(vi, mul_rn(a, xi)); });
 }
 int thsp_add2_scaled_f64(int64_t n, double a, const double* x, double b, const double* y, double* v, thsp_stream_t stream)
 {
@@ -323,10 +399,10 @@ int thsp_add2_scaled_f64(int64_t n, double a, const double* x, double b, const d
     if (a == 0) return thsp_add_scaled_f64(n, b, y, v, stream);
     if (b == 0) return thsp_add_scaled_f64(n, a, x, v, stream);
     if (a == 1)
-        return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], add_rn(x[i], mul_rn(b, y[i]))); });
+        return launch_map<3>(n, s, v, v, x, y, [=] __device__(double vi, double xi, double yi) { return add_rn(vi, add_rn(xi, mul_rn(b, yi))); });
     if (b == 1)
-        return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], add_rn(mul_rn(a, x[i]), y[i])); });
-    return launch_ew(n, s, [=] __device__(int64_t i) { v[i] = add_rn(v[i], add_rn(mul_rn(a, x[i]), mul_rn(b, y[i]))); });
+        return launch_map<3>(n, s, v, v, x, y, [=] __device__(double vi, double xi, double yi) { return add_rn(vi, add_rn(mul_rn(a, xi), yi)); });
+    return launch_map<3>(n, s, v, v, x, y, [=] __device__(double vi, double xi, double yi) { return add_rn(vi, add_rn(mul_rn(a, xi), mul_rn(b, yi))); });
 }
 
 int thsp_check_vector_f64(int64_t nx, const double* x, int64_t ny, const double* y, int* ok_host, thsp_stream_t stream)
