@@ -20,6 +20,8 @@
 // The packed `diagonal` (row==col entries in COO order) is a stable stream compaction.
 // Everything here is integer/byte work bound by HBM traffic.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -718,6 +720,198 @@ static int pack_diagonal(int nnz, const int* ri, const int* ci, const double* va
     return 0;
 }
 
+// ======================================== entries already ordered by the OTHER index: a transpose ======
+// COO -> CSC of a matrix whose entries come row by row (every stencil generator, every .mtx file written from a CSR),
+// and COO -> CSR of one that comes column by column.  The radix sort moves such a matrix three times (256^3 stencil,
+// 449 M entries: 17.2 ms).  But a stable sort by key only has to put every entry into its bucket and order each
+// bucket by ENTRY NUMBER, and when the entries of a bucket come from a narrow band of the input, the slots of the buckets
+// being filled fit L2:
+//   A  count the entries of every bucket with one RED per entry (neighbouring entries hit neighbouring counters),
+//      checking on the way that the other index never decreases, every key is in range, and how far key and other
+//      index lie apart at most (the half band width);
+//   -  scan the counts into the pointers, take the longest bucket;
+//   B  every entry takes the next free slot of its bucket (ATOM on a cursor that starts at the bucket's pointer) and
+//      leaves its ENTRY NUMBER there - 4 bytes, in the array that will hold the other indices: right bucket, arbitrary
+//      order inside it.  (The first version wrote the other index and the value, 12 bytes in two arrays: 8.9 ms of this
+//      pass on the stencil, 11.3 + 9.5 GB of DRAM traffic for 7.2 + 5.4 - the partly written sectors of a 42 MB window
+//      do not survive in L2 until the bucket's next burst of entries arrives 65536 rows later; an evict-first policy on
+//      the input changed nothing.)
+//   C  a CTA stages the entry numbers of its buckets in shared memory, a thread sorts its bucket (insertion sort: the
+//      slots were taken nearly in order), then the CTA fetches other index and value of every entry and writes its
+//      piece of both output arrays with coalesced stores.
+// Sorting by entry number IS the stable order, duplicates included (src/matrix.cpp:139-143), whatever order the atomics
+// ran in.  Buckets longer than kTrMaxLen entries (hub columns), input whose other index decreases somewhere, and bands
+// too wide for L2 go to the radix sort, whose cost does not depend on the shape.
+static constexpr int kTrThreads = 256;   // all of them stage, fetch and write; the first bpc (<= 128) sort a bucket each
+static constexpr int kTrStage = 4096;    // entry numbers staged per CTA (16 KB)
+static constexpr int kTrMaxLen = 64;     // longest bucket a thread sorts by insertion
+static constexpr int kTrWindowBytes = 56 << 20;   // 2 * band * mean bucket * 12 B: the stretch of the output a bucket's entries arrive
+                                                  // over; the 256^3 stencil (42 MB) is the largest that was measured
+static std::atomic<int> g_last_path{0};  // 0 identity, 1 sort, 2 transpose, 3 transpose given up for the sort
+
+// bad[0] |= order broken / key out of range; bad[2] = max |key - oth| (the half band width).  kCount == false: only look
+// (the probe of the first stretch).
+template <bool kCount>
+__global__ void __launch_bounds__(256) tr_count_kernel(int n, int nbuckets, const int* __restrict__ key, const int* __restrict__ oth,
+                                                       int* __restrict__ cnt, int* __restrict__ bad)
+{
+    const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    int b = 0, w = 0;
+    if (base < n) {
+        int k[4], o[5];
+        if (base + 4 <= n && ((((uintptr_t)key) | ((uintptr_t)oth)) & 15) == 0) {
+            const int4 kv = ld_stream4(key + base), ov = ld_stream4(oth + base);
+            k[0] = kv.x; k[1] = kv.y; k[2] = kv.z; k[3] = kv.w;
+            o[0] = ov.x; o[1] = ov.y; o[2] = ov.z; o[3] = ov.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k[j] = base + j < n ? ld_stream(key + base + j) : 0;
+                o[j] = base + j < n ? ld_stream(oth + base + j) : 0x7fffffff;
+            }
+        }
+        o[4] = base + 4 < n ? __ldg(oth + base + 4) : 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (base + j < n) {
+                if (o[j] > o[j + 1] && base + j + 1 < n) b = 1;
+                if ((unsigned)k[j] < (unsigned)nbuckets) {
+                    if (kCount) atomicAdd(cnt + k[j], 1);
+                    w = max(w, abs(k[j] - o[j]));
+                } else {
+                    b = 1;
+                }
+            }
+        }
+    }
+    // one atomic per CTA and only when it raises the value (an atomic per warp on this one address took 3.8 ms of the pass)
+    __shared__ int s_w[8];
+    w = __reduce_max_sync(0xffffffffu, w);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+    const int any_bad = __syncthreads_or(b);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) w = max(w, s_w[i]);
+        if (w > *reinterpret_cast<volatile int*>(bad + 2)) atomicMax(bad + 2, w);
+        if (any_bad) atomicOr(bad, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) tr_place_kernel(int n, const int* __restrict__ key, int* __restrict__ cursor,
+                                                       int* __restrict__ slot_entry)
+{
+    const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (base >= n) return;
+    int k[4], slot[4];
+    const uint64_t pol = policy_evict_first();   // the keys stream through once: L2 is for the cursors and the slots being filled
+    if (base + 4 <= n && (((uintptr_t)key) & 15) == 0) {
+        const int4 kv = ld_stream4_ef(key + base, pol);
+        k[0] = kv.x; k[1] = kv.y; k[2] = kv.z; k[3] = kv.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k[j] = base + j < n ? ld_stream_ef(key + base + j, pol) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) slot[j] = (base + j < n) ? atomicAdd(cursor + k[j], 1) : -1;   // keys were range-checked by the count
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (slot[j] >= 0) slot_entry[slot[j]] = (int)(base + j);
+}
+
+// bpc buckets per CTA (a power of two between 32 and 128, picked from the mean bucket length so that a CTA's entries
+// fit the stage).  io holds the entry numbers on entry and the other indices on return; a bucket that does not fit the
+// stage whole is handled by its thread where it lies in global memory.
+__global__ void __launch_bounds__(kTrThreads) tr_sort_kernel(int nbuckets, int bpc, const int* __restrict__ ptr,
+                                                             const int* __restrict__ oth, const double* __restrict__ val,
+                                                             int* __restrict__ io, double* __restrict__ out_val)
+{
+    __shared__ int s_e[kTrStage];
+    const int b0 = blockIdx.x * bpc;
+    const int nb = min(bpc, nbuckets - b0);
+    const int e0 = ptr[b0], e1 = ptr[b0 + nb];
+    const int staged = min(e1 - e0, kTrStage);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < staged; i += kTrThreads) s_e[i] = io[e0 + i];
+    const bool mine = (int)threadIdx.x < nb;
+    const int s = mine ? ptr[b0 + threadIdx.x] : e1;
+    const int len = mine ? ptr[b0 + threadIdx.x + 1] - s : 0;
+    const bool fits = mine && (s + len - e0 <= staged);
+    const int nfit = __syncthreads_count(fits);   // buckets are contiguous: the ones that fit are the first nfit (barrier: stage complete)
+    if (mine) {
+        int* E = fits ? s_e + (s - e0) : io + s;
+        for (int i = 1; i < len; ++i) {   // insertion sort: the slots were taken nearly in entry order
+            const int ei = E[i];
+            int j = i;
+            while (j > 0 && E[j - 1] > ei) {
+                E[j] = E[j - 1];
+                --j;
+            }
+            if (j != i) E[j] = ei;
+        }
+        if (!fits)
+            for (int i = 0; i < len; ++i) {
+                const int e = E[i];
+                E[i] = __ldg(oth + e);
+                out_val[s + i] = __ldg(val + e);
+            }
+    }
+    __syncthreads();
+    const int wb = (nfit > 0 ? ptr[b0 + nfit] : e0) - e0;   // the buckets handled in global memory lie past this point
+#pragma unroll 4
+    for (int i = threadIdx.x; i < wb; i += kTrThreads) {
+        const int e = s_e[i];
+        io[e0 + i] = __ldg(oth + e);
+        out_val[e0 + i] = __ldg(val + e);
+    }
+}
+
+// 0 = done, 1 = error, 2 = not applicable (the caller sorts): oth decreases somewhere, a key is out of range, a bucket
+// is longer than kTrMaxLen, or the entries of a bucket lie further apart than L2 holds (2 * max|key - oth| buckets of
+// mean length, 12 bytes an entry, against kTrWindowBytes).
+static int transpose_entries(int nbuckets, int nnz, const int* key, const int* oth, const double* val, int* ptr, int* out_oth,
+                             double* out_val, cudaStream_t s, int* tried)
+{
+    *tried = 0;   // set once the probe of the first stretch has let the matrix through
+    if (nbuckets <= 0) return 2;
+    int* cnt = static_cast<int*>(scratch(sizeof(int) * ((size_t)nbuckets + 4), 7));
+    int* flag = static_cast<int*>(scratch(sizeof(int) * 4, 1));
+    if (!cnt || !flag) return 1;
+    int* mx = cnt + nbuckets;   // [0] longest bucket
+    THSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, s));
+    // the first stretch tells most matrices apart: entries not row by row, or spread over the whole width (a uniform
+    // random matrix written row by row: every slot and every cursor would miss L2 - 15 ms for 128 M entries against 5 ms
+    // for the sort)
+    const double mean = (double)nnz / (double)nbuckets;
+    int h[3] = {0, 0, 0};
+    const int probe = std::min(nnz, 1 << 20);
+    tr_count_kernel<false><<<div_up(probe, 1024), 256, 0, s>>>(probe, nbuckets, key, oth, cnt, flag);
+    THSP_LAUNCH_CHECK();
+    THSP_CUDA(cudaMemcpyAsync(h, flag, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    if (h[0] || 2.0 * h[2] * mean * 12.0 > (double)kTrWindowBytes) return 2;
+    *tried = 1;
+    THSP_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nbuckets + 4), s));
+    THSP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * 4, s));
+    tr_count_kernel<true><<<div_up(nnz, 1024), 256, 0, s>>>(nnz, nbuckets, key, oth, cnt, flag);
+    THSP_LAUNCH_CHECK();
+    max_len_kernel<<<std::min(div_up(nbuckets, 256), sm_count() * 8), 256, 0, s>>>(nbuckets, cnt, mx);
+    THSP_LAUNCH_CHECK();
+    if (exclusive_scan(nbuckets, cnt, ptr, s)) return 1;   // queued before the host looks: the sort path overwrites ptr anyway
+    int longest = 0;
+    THSP_CUDA(cudaMemcpyAsync(h, flag, sizeof(int) * 3, cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaMemcpyAsync(&longest, mx, sizeof(int), cudaMemcpyDeviceToHost, s));
+    THSP_CUDA(cudaStreamSynchronize(s));
+    if (h[0] || longest > kTrMaxLen || 2.0 * h[2] * mean * 12.0 > (double)kTrWindowBytes) return 2;
+    THSP_CUDA(cudaMemcpyAsync(cnt, ptr, sizeof(int) * (size_t)nbuckets, cudaMemcpyDeviceToDevice, s));   // the cursors
+    tr_place_kernel<<<div_up(nnz, 1024), 256, 0, s>>>(nnz, key, cnt, out_oth);
+    THSP_LAUNCH_CHECK();
+    int bpc = 128;
+    while (bpc > 32 && mean * bpc * 1.125 > (double)kTrStage) bpc >>= 1;
+    tr_sort_kernel<<<div_up(nbuckets, bpc), kTrThreads, 0, s>>>(nbuckets, bpc, ptr, oth, val, out_oth, out_val);
+    THSP_LAUNCH_CHECK();
+    return 0;
+}
+
 // COO -> (ptr, other index, value) ordered stably by key: the shared body of COO->CSR and COO->CSC.
 static int coo_to_compressed(int nbuckets, int nnz, const int* key, const int* oth, const double* val, int* ptr, int* out_oth,
                              double* out_val, cudaStream_t s)
@@ -729,11 +923,23 @@ static int coo_to_compressed(int nbuckets, int nnz, const int* key, const int* o
     int unsorted = 0;
     if (keys_unsorted(nnz, key, &unsorted, s)) return 1;
     if (!unsorted) {   // stencil generators, sorted .mtx files: the stable order is the identity
+        g_last_path = 0;
         if (bucket_pointers(nbuckets, nnz, key, ptr, s)) return 1;
         copy_entries_kernel<<<div_up(nnz, 256), 256, 0, s>>>(nnz, oth, val, out_oth, out_val);
         THSP_LAUNCH_CHECK();
         return 0;
     }
+    // entries ordered by the other index (a row-by-row matrix on its way to CSC): transposed without a sort
+    static const int no_transpose = getenv("THSP_NO_TRANSPOSE") ? atoi(getenv("THSP_NO_TRANSPOSE")) : 0;   // measurements only
+    int tried = 0;
+    if (!no_transpose) {
+        const int rc = transpose_entries(nbuckets, nnz, key, oth, val, ptr, out_oth, out_val, s, &tried);
+        if (rc != 2) {
+            g_last_path = 2;
+            return rc;
+        }
+    }
+    g_last_path = tried ? 3 : 1;
     const int *sk, *so;
     const double* sv;
     if (stable_sort_entries(nnz, nbuckets, key, oth, val, out_oth, out_val, &sk, &so, &sv, s)) return 1;
@@ -862,6 +1068,8 @@ int thsp_coo2csc(int nrow, int ncol, int nnz, const int* row_ind, const int* col
     if (ensure_device()) return 1;
     return coo_to_compressed(ncol, nnz, col_ind, row_ind, val, col_ptr, out_row_ind, out_val, as_stream(stream));
 }
+
+int thsp_coo_last_path(void) { return g_last_path.load(); }
 
 int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_stream_t stream)
 {
@@ -1086,9 +1294,12 @@ int thsp_prepare_conversions(int nrow, int ncol, int nnz, thsp_stream_t stream)
     if (!scratch(sizeof(int) * (4 * std::max(256 * (size_t)nblk, (size_t)nrow + (size_t)ncol) / kScanTile + 4096), 5)) return 1;   // scan levels
     const size_t np = ((size_t)nnz + 3) & ~(size_t)3;
     const size_t sort_bytes = 2 * np * (sizeof(double) + 2 * sizeof(int));
+    const size_t cursors = (size_t)std::max(nrow, ncol) + 4;   // transpose_entries
     if (sort_bytes <= ((size_t)2 << 30)) {
         if (!scratch(sort_bytes, 6)) return 1;
-        if (!scratch(sizeof(int) * (256 * (size_t)nblk + 1), 7)) return 1;
+        if (!scratch(sizeof(int) * std::max(256 * (size_t)nblk + 1, cursors), 7)) return 1;
+    } else if (!scratch(sizeof(int) * cursors, 7)) {
+        return 1;
     }
     // ---- every conversion once on a small unsorted matrix with a few diagonals
     const int n = 48, m = 96;
@@ -1123,6 +1334,15 @@ int thsp_prepare_conversions(int nrow, int ncol, int nnz, thsp_stream_t stream)
         if (!rc) rc = thsp_csr2dia_fill(n, n, ptr, oci, ova, nd, off, eva, stream);
     }
     if (!rc) rc = thsp_coo2csc(n, n, m, ri, ci, va, ptr, oci, ova, stream);
+    if (!rc) {   // and once row by row, which takes COO->CSC through transpose_entries
+        for (int k = 0; k < m; ++k) {
+            hri[k] = k / 2;
+            hci[k] = (k / 2 + (k % 2 ? n - 1 : 1)) % n;
+        }
+        THSP_CUDA(cudaMemcpyAsync(ri, hri, sizeof(hri), cudaMemcpyHostToDevice, s));
+        THSP_CUDA(cudaMemcpyAsync(ci, hci, sizeof(hci), cudaMemcpyHostToDevice, s));
+        rc = thsp_coo2csc(n, n, m, ri, ci, va, ptr, oci, ova, stream);
+    }
     if (!rc) rc = thsp_coo2ell_prepare(n, n, m, ri, ci, va, &width, stream);
     if (!rc && width > 0 && width <= 8) rc = thsp_coo2ell(n, n, m, ri, ci, va, width, eci, eva, dg, nullptr, stream);
     cudaStreamSynchronize(s);

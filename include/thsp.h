@@ -196,6 +196,13 @@ THSP_API int thsp_coo2csr(int nrow, int ncol, int nnz, const int* row_ind, const
 /* CSCMatrix::CSCMatrix(const COOMatrix&) (src/matrix.cpp:295-325). */
 THSP_API int thsp_coo2csc(int nrow, int ncol, int nnz, const int* row_ind, const int* col_ind, const double* val,
                           int* col_ptr, int* out_row_ind, double* out_val, thsp_stream_t stream);
+/* Which way the last thsp_coo2csr / thsp_coo2csc of this process went (for tests and traces): 0 = keys already
+ * ordered, entries copied through; 1 = stable radix sort; 2 = entries ordered by the OTHER index within a band that
+ * fits L2 (a row-by-row stencil or banded matrix on its way to CSC): per-bucket cursors and a per-bucket sort by entry
+ * number, no radix sort; 3 = the same tried and given up for the radix sort after the first pass (a bucket longer than
+ * 64 entries, an index out of range, the order breaking or the band widening later in the arrays).  The output arrays
+ * are the same bits whichever way it went. */
+THSP_API int thsp_coo_last_path(void);
 /* ELLMatrix::ELLMatrix(const COOMatrix&) (src/matrix.cpp:450-500) in two steps because the
  * caller must allocate nrow*width slots: width = longest row, then the fill. Synchronous. */
 THSP_API int thsp_coo2ell_width(int nrow, int nnz, const int* row_ind, int* width, thsp_stream_t stream);

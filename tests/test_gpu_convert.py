@@ -263,3 +263,116 @@ def test_generators_match_cpu_twins(thsp, cuda, oracle):
     Rm = H.rmat_coo(14, 50000, 42); rri, rci, rva = oracle.gen_rmat_coo(14, 50000, 42)
     assert_bits(host(Rm.row_ind), rri, "rmat ri"); assert_bits(host(Rm.col_ind), rci, "rmat ci"); assert_bits(host(Rm.values), rva, "rmat va")
     assert_bits(host(H.gen_vector(10007, 5).values), oracle.gen_vector(10007, 5), "vec")
+
+
+def _sorted_by_row_no_dups(rs, nrow, ncol, nnz):
+    """nnz distinct (row, col) pairs in row order, the columns of a row in a shuffled order."""
+    lin = np.unique(rs.randint(0, nrow * ncol, nnz, dtype=np.int64))
+    rs.shuffle(lin)
+    ri = (lin // ncol).astype(np.int32); ci = (lin % ncol).astype(np.int32)
+    o = np.argsort(ri, kind="stable")
+    return ri[o], ci[o], rs.uniform(-1, 1, len(o))
+
+
+@pytest.mark.parametrize("case", ["lap5", "stencil27", "shuffled_columns", "column_by_column_to_csr", "tails", "one_row",
+                                  "stage_overflow", "length_64", "length_65", "duplicates", "order_breaks_late",
+                                  "index_out_of_range_free", "empty_buckets", "too_wide_for_l2"])
+def test_transposed_conversions(thsp, cuda, oracle, case):
+    """COO -> CSC of entries that come row by row (and COO -> CSR of entries that come column by column) skips the radix
+    sort: per-bucket cursors + a per-bucket sort by entry number (convert.cu, transpose_entries).  Same arrays as the
+    reference's counting sort (src/matrix.cpp:295-325 / 115-154) bit for bit, whichever way the call went; the way it
+    went is checked too (thsp_coo_last_path: 2 = transposed, 3 = tried and handed to the sort)."""
+    from arm_spmv_b200 import host as H
+    import zlib
+    lib = thsp.load()
+    rs = np.random.RandomState(zlib.crc32(case.encode()))
+    to_csr = False
+    want_path = 2
+    if case == "lap5":
+        nrow = ncol = 257 * 257
+        ri, ci, va = oracle.gen_lap5_coo(257)
+    elif case == "stencil27":
+        rp, cc, vv = oracle.gen_stencil27_csr(33)
+        nrow = ncol = 33 ** 3
+        ri = np.repeat(np.arange(nrow, dtype=np.int32), np.diff(rp)); ci = cc; va = rs.uniform(-1, 1, len(vv))   # not symmetric
+    elif case == "shuffled_columns":
+        nrow, ncol = 50021, 70001
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, 900_000)
+    elif case == "column_by_column_to_csr":
+        ncol, nrow = 50021, 70001
+        ci, ri, va = _sorted_by_row_no_dups(rs, ncol, nrow, 900_000)
+        to_csr = True
+    elif case == "tails":   # entry counts around the four-entry groups of the count / place kernels
+        for nnz in (1, 2, 3, 5, 6, 7, 1023, 1025, 4099):
+            nrow, ncol = 301, 211
+            ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, nnz)
+            Cc = H.CSCMatrix(H.COOMatrix(nrow, ncol, ri, ci, va))
+            cp, ro, cv = oracle.coo2csc(nrow, ncol, ri, ci, va)
+            assert_bits(host(Cc.col_ptr), cp, f"col_ptr {nnz}"); assert_bits(host(Cc.row_ind), ro, f"csc row {nnz}")
+            assert_bits(host(Cc.values), cv, f"csc val {nnz}")
+        return
+    elif case == "one_row":
+        nrow, ncol = 1, 5000
+        ci = rs.permutation(ncol).astype(np.int32)[:3001]; ri = np.zeros(len(ci), np.int32); va = rs.uniform(-1, 1, len(ci))
+    elif case in ("stage_overflow", "length_64", "length_65"):
+        # 300 neighbouring columns of L entries each in a wide, otherwise nearly empty matrix: the mean bucket is short, so a
+        # CTA takes 128 buckets, and 128 * L entries do not fit its 4096-entry stage: the later ones are sorted in place
+        L = {"stage_overflow": 60, "length_64": 64, "length_65": 65}[case]
+        nrow, ncol = L + 7, 200_000
+        cols = 1000 + np.arange(300, dtype=np.int32)
+        ri = np.repeat(np.arange(L, dtype=np.int32), len(cols))
+        ci = np.concatenate([rs.permutation(cols) for _ in range(L)]).astype(np.int32)
+        extra_r = np.full(50, L + 3, np.int32); extra_c = rs.choice(np.arange(5000, 190_000, dtype=np.int32), 50, replace=False)
+        ri = np.concatenate([ri, extra_r]); ci = np.concatenate([ci, extra_c]); va = rs.uniform(-1, 1, len(ri))
+        if case == "length_65":
+            want_path = 3
+    elif case == "duplicates":
+        nrow, ncol = 5003, 4001
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, 60_000)
+        k = len(ri) // 2   # one pair of entries with both indices equal (they sit in the same row, so next to each other)
+        ri = np.insert(ri, k + 1, ri[k]); ci = np.insert(ci, k + 1, ci[k]); va = np.insert(va, k + 1, 0.5)
+        for q in range(0, len(ri) - 3, 1000):   # and whole runs of them here and there: they must keep their COO order
+            ri[q:q + 3] = ri[q]; ci[q:q + 3] = ci[q]
+    elif case == "order_breaks_late":
+        nrow, ncol = 200_003, 150_001
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, 1_300_000)
+        assert len(ri) > (1 << 20) + 1000
+        ri[-7], ri[-400] = ri[-400], ri[-7]   # past the first 2^20 entries, which is all the probe reads
+        want_path = 3
+    elif case == "index_out_of_range_free":   # the largest legal indices
+        nrow, ncol = 77, 91
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, 3000)
+        ri[-1] = nrow - 1; ci[-1] = ncol - 1; ci[0] = 0
+        lin = ri.astype(np.int64) * ncol + ci
+        if len(np.unique(lin)) != len(lin):
+            want_path = None
+    elif case == "too_wide_for_l2":   # row by row, but a column's entries come from all over the matrix: the probe sends it to the sort
+        nrow = ncol = 1 << 22
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, ncol, 3_000_000)
+        want_path = 1
+    else:   # empty_buckets: long stretches of empty columns in front of, between and behind the occupied ones
+        nrow, ncol = 4000, 1 << 22
+        ri, ci, va = _sorted_by_row_no_dups(rs, nrow, 1024, 20_000)
+        ci = (ci.astype(np.int64) * 4001 + 100_000).astype(np.int32)
+        assert int(ci.max()) < ncol
+    A = H.COOMatrix(nrow, ncol, ri, ci, va)
+    if to_csr:
+        B = H.CSRMatrix(A)
+        path = lib.thsp_coo_last_path()
+        rp, co, cv, dg = oracle.coo2csr(nrow, ncol, ri, ci, va)
+        assert_bits(host(B.row_ptr), rp, "row_ptr"); assert_bits(host(B.col_ind), co, "csr col"); assert_bits(host(B.values), cv, "csr val")
+        assert B.ndiag == len(dg); assert_bits(host(B.diagonal)[:B.ndiag], dg, "diag")
+    else:
+        Cc = H.CSCMatrix(A)
+        path = lib.thsp_coo_last_path()
+        cp, ro, cv = oracle.coo2csc(nrow, ncol, ri, ci, va)
+        assert_bits(host(Cc.col_ptr), cp, "col_ptr"); assert_bits(host(Cc.row_ind), ro, "csc row"); assert_bits(host(Cc.values), cv, "csc val")
+    if want_path is not None:
+        assert path == want_path, f"conversion went way {path}, expected {want_path}"
+    # the same matrix the other way round keeps its keys: copied through (path 0)
+    if not to_csr:
+        B = H.CSRMatrix(A)
+        if case != "order_breaks_late":
+            assert lib.thsp_coo_last_path() == 0
+        rp, co, cv, dg = oracle.coo2csr(nrow, ncol, ri, ci, va)
+        assert_bits(host(B.row_ptr), rp, "row_ptr"); assert_bits(host(B.col_ind), co, "csr col"); assert_bits(host(B.values), cv, "csr val")
