@@ -742,9 +742,11 @@ static int pack_diagonal(int nnz, const int* ri, const int* ci, const double* va
 // Sorting by entry number IS the stable order, duplicates included (src/matrix.cpp:139-143), whatever order the atomics
 // ran in.  Buckets longer than kTrMaxLen entries (hub columns), input whose other index decreases somewhere, and bands
 // too wide for L2 go to the radix sort, whose cost does not depend on the shape.
-static constexpr int kTrThreads = 256;   // all of them stage, fetch and write; the first bpc (<= 128) sort a bucket each (128-thread CTAs,
-                                         // 14 to an SM: 17.6 ms for the whole conversion on the 256^3 stencil against 10.1)
-static constexpr int kTrStage = 4096;    // entry numbers staged per CTA (16 KB)
+static constexpr int kTrThreads = 512;   // all of them stage, fetch and write; the first half sort a bucket each.  256^3 stencil, whole
+                                         // conversion: 128 threads 9.67 ms, 256 9.44, 512 9.18 (shared memory per SM the same: bigger
+                                         // CTAs keep more of the buckets that share input sectors - columns 256 apart - together);
+                                         // 128-thread CTAs with a 16 KB stage, 14 to an SM, 17.6 ms: no L1 left for the gathers
+static constexpr int kTrStage = 8192;    // entry numbers staged per CTA (32 KB; four CTAs per SM)
 static constexpr int kTrMaxLen = 64;     // longest bucket a thread sorts by insertion
 static constexpr int kTrWindowBytes = 56 << 20;   // 2 * band * mean bucket * 12 B: the stretch of the output a bucket's entries arrive
                                                   // over; the 256^3 stencil (42 MB) is the largest that was measured
@@ -872,18 +874,19 @@ __device__ __forceinline__ void st_once(double* p, double v, uint64_t pol)
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
-// bpc buckets per CTA (a power of two between 32 and 128, picked from the mean bucket length so that a CTA's entries
+// bpc buckets per CTA (a power of two between 32 and 256, picked from the mean bucket length so that a CTA's entries
 // fit the stage).  io holds the entry numbers on entry and the other indices on return; a bucket that does not fit the
 // stage whole is handled by its thread where it lies in global memory.
-__global__ void __launch_bounds__(kTrThreads) tr_sort_kernel(int nbuckets, int bpc, const int* __restrict__ ptr,
-                                                             const int* __restrict__ oth, const double* __restrict__ val,
-                                                             int* __restrict__ io, double* __restrict__ out_val)
+__global__ void __launch_bounds__(512) tr_sort_kernel(int nbuckets, int bpc, int stage, const int* __restrict__ ptr,
+                                                      const int* __restrict__ oth, const double* __restrict__ val,
+                                                      int* __restrict__ io, double* __restrict__ out_val)
 {
-    __shared__ int s_e[kTrStage];
+    extern __shared__ int s_e[];   // stage entry numbers
+    const int kTrThreads = blockDim.x;
     const int b0 = blockIdx.x * bpc;
     const int nb = min(bpc, nbuckets - b0);
     const int e0 = ptr[b0], e1 = ptr[b0 + nb];
-    const int staged = min(e1 - e0, kTrStage);
+    const int staged = min(e1 - e0, stage);
     // entry numbers in and both output arrays out pass through once; what should stay in L2 is the stretch of the input the
     // gathers below come back to (a sector of it serves several buckets of several CTAs)
     const uint64_t pol = policy_evict_first();
@@ -954,9 +957,14 @@ static int transpose_entries(int nbuckets, int nnz, const int* key, const int* o
     THSP_CUDA(cudaMemcpyAsync(cnt, ptr, sizeof(int) * (size_t)nbuckets, cudaMemcpyDeviceToDevice, s));   // the cursors
     tr_place_kernel<<<div_up(nnz, 1024), 256, 0, s>>>(nnz, key, cnt, out_oth);
     THSP_LAUNCH_CHECK();
-    int bpc = 128;
-    while (bpc > 32 && mean * bpc * 1.125 > (double)kTrStage) bpc >>= 1;
-    tr_sort_kernel<<<div_up(nbuckets, bpc), kTrThreads, 0, s>>>(nbuckets, bpc, ptr, oth, val, out_oth, out_val);
+    // CTA shape: T threads stage, fetch and write, the first T/2 sort a bucket each, 16 T entry numbers of shared memory -
+    // 128 KB and 2048 threads per SM whatever T is.  THSP_TR_THREADS = 128 / 256 / 512 for measurements.
+    static const int env_threads = getenv("THSP_TR_THREADS") ? atoi(getenv("THSP_TR_THREADS")) : 0;
+    const int threads = (env_threads == 128 || env_threads == 256) ? env_threads : kTrThreads;
+    const int stage = kTrStage / kTrThreads * threads;
+    int bpc = threads / 2;
+    while (bpc > 32 && mean * bpc * 1.125 > (double)stage) bpc >>= 1;
+    tr_sort_kernel<<<div_up(nbuckets, bpc), threads, sizeof(int) * (size_t)stage, s>>>(nbuckets, bpc, stage, ptr, oth, val, out_oth, out_val);
     THSP_LAUNCH_CHECK();
     return 0;
 }

@@ -41,7 +41,7 @@ def row(name, A):
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 row("lap5 1024^2 (configs[0])", H.lap5_coo(1024))
 row(f"stencil27 {n}^3", H.stencil27_coo(n))
-if n >= 256:
+if n >= 256 and len(sys.argv) <= 2:
     # configs[3]'s matrix ordered by row (what a CSR-written file of it looks like): random columns, no locality
     A = H.uniform_coo(1 << 23, 1 << 23, 1 << 27, 43)
     o = torch.sort(A.row_ind.long() * (1 << 23) + A.col_ind.long()).indices

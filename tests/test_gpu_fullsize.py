@@ -112,6 +112,24 @@ def test_conversions_full_size_are_the_stable_sort(thsp, cuda, which):
     _check_compressed(H, A.ncol, A.col_ind, A.row_ind, A.values, Cc.col_ptr, Cc.row_ind, Cc.values)
 
 
+def test_stencil_256_coo_to_csc_is_transposed_not_sorted(thsp, cuda):
+    """configs[1] as a COO matrix (449 M entries, row by row): COO -> CSC goes through transpose_entries (convert.cu:
+    per-column cursors, entry numbers in the slots, per-column sort, gather), not through the radix sort, and its arrays are
+    the stable sort by column bit for bit (values = original position, so the output shows the permutation itself).
+    src/matrix.cpp:295-325."""
+    from arm_spmv_b200 import host as H
+    A = H.stencil27_coo(256)
+    A.values.copy_(torch.arange(A.nnz, dtype=torch.float64, device="cuda"))
+    Cc = H.CSCMatrix(A)
+    assert thsp.load().thsp_coo_last_path() == 2
+    order = _check_compressed(H, A.ncol, A.col_ind, A.row_ind, A.values, Cc.col_ptr, Cc.row_ind, Cc.values)
+    assert torch.equal(Cc.values.to(torch.int64), order)
+    del order, Cc
+    B = H.CSRMatrix(A)   # the keys are in order already: copied through
+    assert thsp.load().thsp_coo_last_path() == 0
+    assert torch.equal(B.col_ind, A.col_ind) and torch.equal(B.values, A.values)
+
+
 @pytest.mark.parametrize("which", ["uniform", "rmat"])
 def test_spmv_full_size_formats_agree(thsp, cuda, which):
     """Every CSR kernel, COO and CSC on the full-size irregular matrices against the in-order scalar CSR kernel
