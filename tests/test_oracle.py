@@ -191,3 +191,26 @@ def test_symgs_and_cg_restatements(oracle):
     y = oracle.gen_vector(777, 9)
     assert oracle.tree_sum(oracle.tile_sumsq(y)) == oracle.dot_canonical(y, y)
     assert (oracle.hash_f64(y[:300], 10) + oracle.hash_f64(y[300:], 310)) % (1 << 64) == oracle.hash_f64(y, 10)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_buckets_ordered_by_entry_number_are_the_counting_sort(oracle, seed):
+    """What the GPU's transposing conversion relies on (convert.cu, transpose_entries): drop every entry into its
+    column in ANY order, then order each column by entry number - that is the reference's counting sort
+    (src/matrix.cpp:295-325), duplicates included.  The arrival order of the atomics is played by a random permutation."""
+    rs = np.random.RandomState(seed)
+    nrow, ncol, nnz = 300, 200, 5000
+    ri = np.sort(rs.randint(0, nrow, nnz)).astype(np.int32)
+    ci = rs.randint(0, ncol, nnz).astype(np.int32)          # (row, col) pairs repeat: 5000 draws from 60000 cells
+    va = rs.uniform(-1, 1, nnz)
+    cp, ro, vo = oracle.coo2csc(nrow, ncol, ri, ci, va)
+    counts = np.bincount(ci, minlength=ncol)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    cursor = ptr[:-1].copy()
+    slot_entry = np.full(nnz, -1, np.int64)
+    for e in rs.permutation(nnz):                            # the order the atomics happen to run in
+        slot_entry[cursor[ci[e]]] = e
+        cursor[ci[e]] += 1
+    for c in range(ncol):
+        slot_entry[ptr[c]:ptr[c + 1]].sort()                 # per-bucket sort by entry number
+    eq(ptr, cp); eq(ri[slot_entry], ro); eq(va[slot_entry], vo)
