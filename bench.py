@@ -228,6 +228,15 @@ def cpu_reference_arm(n, reps, warm=1, iterated=False, want_y=None):
     return 2.0 * nnz / dt / 1e9, dt, kind, cores, sample, tuned
 
 
+def n1_config(n, nnz=None):
+    """`config` of the N = 1 line, the same dict in both arms (ours and --impl reference): the workload, not how an arm runs it."""
+    N = n ** 3
+    nnz = (3 * n - 2) ** 3 if nnz is None else int(nnz)
+    nbytes = nnz * 12 + (N + 1) * 4 + 3 * N * 8
+    return {"workload": f"fp64 CSR SpMV (y += A x), 27-point stencil {n}^3 (BASELINE configs[1])", "rows": N, "nnz": nnz,
+            "cache": f"inputs ({nbytes / 1e9:.1f} GB) larger than the GPU's L2 (126 MB) and every host cache"}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -245,7 +254,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(gf, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 4), "higher_is_better": True,
         "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "grid": n, "rows": N},
+        "config": {"workload": workload, "grid": n, "rows": N} if multi else n1_config(n),
+        "arm_detail": {"what": workload, "grid": n},
         "cpu_baseline": {"value": round(gf, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(gf, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -447,9 +457,9 @@ def run_single(args):
         "metric": METRIC, "value": round(gflops, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"fp64 CSR SpMV (y += A x), 27-point stencil {n}^3 generated on device (BASELINE configs[1])",
-                   "rows": N, "nnz": nnz, "kernel": kname, "lanes": lanes, "cache": "inputs (5.9 GB) larger than L2 (126 MB)",
-                   "step_ms_min": round(min(per), 5), "step_ms_max": round(max(per), 5)},
+        "config": n1_config(n, nnz),
+        "arm_detail": {"matrix": "generated on device", "kernel": kname, "lanes": lanes,
+                       "step_ms_min": round(min(per), 5), "step_ms_max": round(max(per), 5)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": bytes_alg, "frac_of_8TBs_spec": round(achieved / 8000.0, 4)},
